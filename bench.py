@@ -1,0 +1,411 @@
+#!/usr/bin/env python
+"""bench.py -- circuit throughput of the B200 state-vector gate path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload variational|qft|supremacy|qv]
+                    [--nqubits n] [--dtype complex128|complex64] [--fuse k] [--impl reference]
+
+A "step" is one full execution of the workload circuit: |0..0> preparation followed by every
+gate (fused into blocks of at most --fuse qubits).  The default workload is BASELINE.json's
+configs[1]: the variational RY+CZ circuit on 30 qubits in complex128 with gate fusion, on one
+B200.  `value` is gates/s with the circuit program resident (state and kernels on the device,
+gate matrices already built); `e2e` is the same metric through the public backend API
+(`execute_circuit` from host gate objects: host matrices go down with every launch, a marginal
+probability vector comes back every step).  `roofline` is measured live with CUDA events around
+every launch of the timed steps; `cpu_baseline` times the CPU oracle (a C/OpenMP port of the
+reference's numba kernels) on this box's host cores on a bounded sample of the same gate list.
+
+`--impl reference` runs that CPU port alone (the reference itself is Python+numba+qibo and
+cannot be installed offline) and prints the same JSON line.
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+DEFAULTS = {
+    "variational": dict(nqubits=30, dtype="complex128", fuse=4),
+    "qft": dict(nqubits=33, dtype="complex128", fuse=1),
+    "supremacy": dict(nqubits=32, dtype="complex64", fuse=4),
+    "qv": dict(nqubits=32, dtype="complex64", fuse=2),
+}
+
+
+def build_circuit(workload, nqubits):
+    from qibojit_b200 import circuits
+
+    if workload == "variational":
+        return circuits.variational(nqubits)
+    if workload == "qft":
+        return circuits.qft(nqubits)
+    if workload == "supremacy":
+        return circuits.supremacy(nqubits)
+    if workload == "qv":
+        return circuits.quantum_volume(nqubits)
+    raise ValueError(workload)
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.samples = []
+        self._stop = threading.Event()
+        self._thread = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(
+                    ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                     "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        self._thread.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names)
+                   if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------- CPU arm
+def oracle_program(circuit):
+    """Lower gate objects to calls of the CPU oracle (same dispatch as the reference backend)."""
+    from oracle import oracle as O
+    from qibojit_b200.backends.b200 import GATE_OPS
+    from qibojit_b200.matrices import CustomMatrices
+    from tests import refdispatch as R
+
+    n = circuit.nqubits
+    prog = []
+    for g in circuit.queue:
+        name = g.__class__.__name__
+        t = g.target_qubits
+        q = R.qubits_tensor(n, t, g.control_qubits)
+
+        def mat(dtype, g=g, name=name):
+            from qibojit_b200 import fusion
+            mats = CustomMatrices(dtype)
+            if name == "FusedGate":
+                return fusion.fused_matrix(g, mats)
+            return g.target_matrix(mats)
+
+        if len(t) == 1:
+            op = GATE_OPS.get(name, "apply_gate")
+            prog.append(lambda st, dt, t=t, op=op, mat=mat, q=q, g=g: R.one_qubit_base(
+                O, st, n, t[0], op, mat(dt), q if g.control_qubits else None))
+        elif len(t) == 2:
+            op = GATE_OPS.get(name, "apply_two_qubit_gate")
+            prog.append(lambda st, dt, t=t, op=op, mat=mat, q=q, g=g: R.two_qubit_base(
+                O, st, n, t[0], t[1], op, mat(dt), q if g.control_qubits else None))
+        else:
+            prog.append(lambda st, dt, t=t, mat=mat, q=q: R.multi_qubit_base(O, st, n, list(t), mat(dt), q))
+    return prog
+
+
+def cpu_sample(workload, nqubits, dtype, budget_s, fuse):
+    """Time the oracle on a bounded sample: the first gates of the same (unfused, as the
+    reference executes it by default) circuit at the largest n <= nqubits that fits host RAM,
+    until `budget_s` seconds are spent.  Returns (gates/s, description, cores)."""
+    import psutil
+
+    from oracle import oracle as O
+
+    amp = 16 if dtype == "complex128" else 8
+    avail = psutil.virtual_memory().available
+    n = nqubits
+    while (amp << n) > 0.6 * avail and n > 20:
+        n -= 1
+    circuit = build_circuit(workload, n)
+    if fuse > 1:  # qibo's default fusion width for the numba backend is two qubits
+        circuit = circuit.fuse(max_qubits=2)
+    weights = [len(getattr(g, "gates", [g])) for g in circuit.queue]
+    total_gates = sum(weights)
+    prog = oracle_program(circuit)
+    cores = O.max_threads()
+    st = np.empty(1 << n, dtype=dtype)
+    O.initial_state_vector(st)
+    prog[0](st, dtype)  # warm up (page faults, thread pool)
+    O.initial_state_vector(st)
+    t0 = time.perf_counter()
+    done = 0
+    for call, w in zip(prog, weights):
+        call(st, dtype)
+        done += w
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    gps = done / dt
+    how = "fused to 2-qubit blocks as qibo does by default" if fuse > 1 else "unfused"
+    desc = (f"first {done} of {total_gates} gates of {workload}-{n} {dtype} ({how}) in {dt:.1f}s"
+            f" on {cores} threads")
+    if n != nqubits:
+        scale = 2.0 ** (n - nqubits)
+        desc += f"; n reduced from {nqubits} to fit host RAM, value scaled by 2^{n - nqubits}"
+        gps *= scale
+    return gps, desc, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = DEFAULTS[args.workload]
+    nqubits = args.nqubits or cfg["nqubits"]
+    dtype = args.dtype or cfg["dtype"]
+    t0 = time.perf_counter()
+    per_step = max(5.0, min(30.0, 150.0 / max(1, args.steps + args.warmup)))
+    vals = []
+    desc, cores = "", 1
+    for i in range(args.warmup + args.steps):
+        gps, desc, cores = cpu_sample(args.workload, nqubits, dtype, per_step, cfg["fuse"])
+        if i >= args.warmup:
+            vals.append(gps)
+    value = float(np.mean(vals))
+    line = {
+        "impl": "reference", "metric": "gates_per_second", "value": value, "unit": "gates/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * (time.perf_counter() - t0) / max(1, args.steps + args.warmup),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64" if dtype == "complex128" else "f32",
+        "data": "synthetic",
+        "config": {"workload": f"{args.workload}-{nqubits}-{dtype}", "fusion_max_qubits": min(2, cfg["fuse"]),
+                   "note": "CPU port (oracle/qj_oracle.c, C+OpenMP) of the reference numba kernels"},
+        "cpu_baseline": {"value": value, "unit": "gates/s", "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": "gates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------- GPU arm
+def lower_program(backend, circuit, dtype):
+    """Pre-bind every gate of the (fused) circuit to a backend call with its host matrix built,
+    and attach the algorithmic bytes of the pass."""
+    n = circuit.nqubits
+    amp = 16 if dtype == "complex128" else 8
+    nbytes_state = amp << n
+    from qibojit_b200.backends.b200 import GATE_OPS
+
+    prog = []
+    for g in circuit.queue:
+        name = g.__class__.__name__
+        c = len(g.control_qubits)
+        op = GATE_OPS.get(name)
+        if op in ("apply_z", "apply_z_pow"):
+            alg = 2 * nbytes_state / 2 ** (c + 1)
+            kind = "diag"
+        elif op == "apply_swap":
+            alg = 2 * nbytes_state / 2 ** (c + 1)
+            kind = "swap"
+        elif op == "apply_fsim":
+            alg = 1.5 * nbytes_state / 2 ** c
+            kind = "fsim"
+        else:
+            alg = 2 * nbytes_state / 2 ** c
+            kind = f"dense{len(g.target_qubits)}" + (f"c{c}" if c else "")
+            if op in ("apply_x", "apply_y"):
+                kind = "perm" + (f"c{c}" if c else "")
+        matrix = backend._as_custom_matrix(g)
+        qubits = backend._create_qubits_tensor(g, n)
+        prog.append((g, matrix, qubits, kind, alg))
+    return prog
+
+
+def run_program(backend, prog, state, n, events=None):
+    import torch
+
+    from qibojit_b200.backends.b200 import GATE_OPS
+
+    for i, (g, matrix, qubits, kind, alg) in enumerate(prog):
+        if events is not None:
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+        t = g.target_qubits
+        name = g.__class__.__name__
+        if len(t) == 1:
+            backend._one_qubit_base(state, n, t[0], GATE_OPS.get(name, "apply_gate"), matrix, qubits)
+        elif len(t) == 2:
+            backend._two_qubit_base(state, n, t[0], t[1], GATE_OPS.get(name, "apply_two_qubit_gate"), matrix, qubits)
+        else:
+            backend._multi_qubit_base(state, n, t, matrix, qubits)
+        if events is not None:
+            e1.record()
+            events.append((kind, alg, e0, e1))
+    return state
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from qibojit_b200.backends.b200 import B200Backend
+
+    cfg = DEFAULTS[args.workload]
+    nqubits = args.nqubits or cfg["nqubits"]
+    dtype = args.dtype or cfg["dtype"]
+    fuse = args.fuse or cfg["fuse"]
+    backend = B200Backend()
+    backend.set_dtype(dtype)
+
+    if world > 1:
+        from bench_distributed import run_distributed
+
+        return run_distributed(args, backend, nqubits, dtype, fuse, world, rank)
+
+    circuit = build_circuit(args.workload, nqubits)
+    ngates = circuit.ngates
+    fused = circuit.fuse(max_qubits=fuse) if fuse > 1 else circuit
+    prog = lower_program(backend, fused, dtype)
+    amp = 16 if dtype == "complex128" else 8
+
+    state = backend.zero_state(nqubits)
+
+    def step(events=None):
+        import ctypes
+        from qibojit_b200 import _capi
+        _capi.check(backend._lib.qj_initial_state(backend._handle(), state.data_ptr(), backend._tag(state), nqubits))
+        run_program(backend, prog, state, nqubits, events)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    launches0 = backend.launch_count()
+    events = []
+    t_start = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        torch.cuda.synchronize()
+        t_start.record()
+        for _ in range(args.steps):
+            step(events)
+        t_end.record()
+        torch.cuda.synchronize()
+    total_ms = t_start.elapsed_time(t_end)
+    launches = backend.launch_count() - launches0
+    ms_per_step = total_ms / args.steps
+    value = ngates / (ms_per_step * 1e-3)
+
+    # roofline of the dominant kernel class, from the per-launch events of the timed steps
+    per_kind = {}
+    for kind, alg, e0, e1 in events:
+        d = per_kind.setdefault(kind, {"ms": 0.0, "bytes": 0.0, "n": 0})
+        d["ms"] += e0.elapsed_time(e1)
+        d["bytes"] += alg
+        d["n"] += 1
+    dom = max(per_kind, key=lambda k: per_kind[k]["ms"])
+    peak, peak_src = measured_peak_gbs()
+    achieved = per_kind[dom]["bytes"] / (per_kind[dom]["ms"] * 1e-3) / 1e9
+    breakdown = {k: {"launches_per_step": v["n"] // args.steps, "avg_ms": v["ms"] / v["n"],
+                     "gbs": v["bytes"] / (v["ms"] * 1e-3) / 1e9} for k, v in per_kind.items()}
+
+    # end to end through the public API: host gate objects in, marginal probabilities out
+    h2d = sum((np.asarray(m).nbytes if m is not None else 0) + q.nbytes for _, m, q, _, _ in prog)
+    e2e_times = []
+    d2h = 0
+    for i in range(1 + min(args.steps, 3)):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out = backend.execute_circuit(fused)
+        probs = backend.calculate_probabilities(out, [0, 1, 2, 3], nqubits)
+        host = probs.cpu().numpy()
+        torch.cuda.synchronize()
+        if i:
+            e2e_times.append(time.perf_counter() - t0)
+        d2h = host.nbytes
+        del out
+    e2e_value = ngates / float(np.mean(e2e_times))
+    assert abs(host.sum() - 1.0) < 1e-6, host.sum()
+
+    cpu_gps, cpu_desc, cores = cpu_sample(args.workload, nqubits, dtype, args.cpu_seconds, fuse)
+
+    line = {
+        "metric": "gates_per_second", "value": value, "unit": "gates/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64" if dtype == "complex128" else "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}-{nqubits}-{dtype}", "circuit_gates": ngates,
+                   "fusion_max_qubits": fuse, "kernel_passes_per_step": len(prog) + 1,
+                   "state_bytes": amp << nqubits,
+                   "l2_policy": "state (>= 16 GiB) is far larger than the 126 MB L2; no flush needed",
+                   "timing": "CUDA events on the launch stream"},
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "per_kernel": breakdown},
+        "cpu_baseline": {"value": cpu_gps, "unit": "gates/s", "cores": cores, "kind": "port", "sample": cpu_desc},
+        "e2e": {"value": e2e_value, "unit": "gates/s", "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(d2h)},
+        "gpu_launches": int(launches),
+        "clocks": clocks.summary(),
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="variational", choices=sorted(DEFAULTS))
+    ap.add_argument("--nqubits", type=int, default=0)
+    ap.add_argument("--dtype", default="")
+    ap.add_argument("--fuse", type=int, default=0)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,150 @@
+/*
+ * qibojit_b200.h -- C ABI of the B200-native state-vector gate path.
+ *
+ * One entry point per kernel that qibojit binds for this path.  "Replaces" lines cite the
+ * reference interface (numba kernel in /root/reference/src/qibojit/custom_operators/ and the
+ * CuPy RawKernel + launcher in .../custom_operators/raw_kernels.py, .../backends/gpu.py).
+ *
+ * Conventions
+ *  - `state` is a DEVICE pointer to 2^nqubits amplitudes, interleaved (re, im);
+ *    dtype QJ_C64 = complex64 (2 x float), QJ_C128 = complex128 (2 x double).
+ *    It must be 32-byte aligned (any cudaMalloc / torch allocation is).
+ *  - `gate` is a HOST pointer to the row-major gate buffer in the state dtype (the
+ *    reference hands a device array, gpu.py:936; here the library stages it itself so that
+ *    no gate costs a device allocation or a synchronisation).
+ *  - `qubits` is a HOST int32 array: sorted ascending index-bit positions (n-1-q) of
+ *    controls U targets, exactly cpu.py:565-569.  NULL / nactive == ntargets selects the
+ *    kernel without controls (cpu.py:612-616, 631-635).
+ *  - every call is asynchronous on the handle's stream; qj_sync() waits.  All kernels work
+ *    in place; nothing state-sized is ever allocated by the library.
+ *  - return value: 0 = ok, negative = error (QJ_ERR_*); qj_last_error() gives the message
+ *    for the calling thread.  Handles are per device and may be used from one thread at a
+ *    time (the reference drives one device per joblib thread, gpu.py:688-694).
+ */
+#ifndef QIBOJIT_B200_H
+#define QIBOJIT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QJ_C64 0
+#define QJ_C128 1
+
+#define QJ_OK 0
+#define QJ_ERR_INVALID (-1) /* bad argument (ValueError upstream, gpu.py:989-993)   */
+#define QJ_ERR_CUDA (-2)    /* CUDA runtime error (RuntimeError upstream, gpu.py:733) */
+#define QJ_ERR_NODEVICE (-3)
+#define QJ_ERR_UNSUPPORTED (-4)
+
+#define QJ_MAX_QUBITS 48       /* index bits addressable by the kernels            */
+#define QJ_MAX_TARGETS 10      /* dense k-target gate limit (reference GPU: 7, gpu.py:48) */
+
+typedef struct qj_handle qj_handle;
+
+/* ---- handle / runtime ------------------------------------------------------------ */
+/* stream: a cudaStream_t created by the caller (e.g. torch's current stream) or NULL to let
+ * the handle own a private non-blocking stream. */
+int qj_create(int device, void *stream, qj_handle **out);
+int qj_destroy(qj_handle *h);
+int qj_set_stream(qj_handle *h, void *stream);
+int qj_sync(qj_handle *h);
+const char *qj_last_error(void);
+const char *qj_version(void);
+/* number of kernels launched through this handle since creation (bench: gpu_launches) */
+int64_t qj_launch_count(qj_handle *h);
+/* kernel routing: 0 = automatic, 1 = force the register ("direct") kernels,
+ * 2 = force the shared-memory tile kernel where it applies.  For tests and profiling. */
+int qj_set_route(qj_handle *h, int route);
+
+/* ---- state preparation -------------------------------------------------------------
+ * replaces ops.initial_state_vector (ops.py:14-18), initial_state_kernel
+ * (raw_kernels.py:548-558) + cp.zeros (gpu.py:584-600).                                 */
+int qj_initial_state(qj_handle *h, void *state, int dtype, int nqubits);
+
+/* ---- one-target kernels ------------------------------------------------------------
+ * replace {,multicontrol_}apply_gate / apply_x / apply_y / apply_z / apply_z_pow
+ * (gates.py:16-114, raw_kernels.py:128-221 and 293-391; launcher gpu.py:1009-1036).
+ * m = index bit of the target.  gate: 2x2 (apply_gate) or one scalar (apply_z_pow).      */
+int qj_apply_gate(qj_handle *h, void *state, int dtype, int nqubits, int m, const void *gate,
+                  const int32_t *qubits, int nactive);
+int qj_apply_x(qj_handle *h, void *state, int dtype, int nqubits, int m,
+               const int32_t *qubits, int nactive);
+int qj_apply_y(qj_handle *h, void *state, int dtype, int nqubits, int m,
+               const int32_t *qubits, int nactive);
+int qj_apply_z(qj_handle *h, void *state, int dtype, int nqubits, int m,
+               const int32_t *qubits, int nactive);
+int qj_apply_z_pow(qj_handle *h, void *state, int dtype, int nqubits, int m, const void *phase,
+                   const int32_t *qubits, int nactive);
+
+/* ---- two-target kernels --------------------------------------------------------------
+ * replace {,multicontrol_}apply_two_qubit_gate / apply_swap / apply_fsim
+ * (gates.py:118-254, raw_kernels.py:224-290 and 394-477; launcher gpu.py:1038-1076).
+ * m1 < m2 are the target index bits, swap_targets as computed in cpu.py:622-629.
+ * gate: 4x4 (two_qubit_gate) or the 5-vector of matrices.py:62-70 (fsim).                */
+int qj_apply_two_qubit_gate(qj_handle *h, void *state, int dtype, int nqubits, int m1, int m2,
+                            int swap_targets, const void *gate, const int32_t *qubits,
+                            int nactive);
+int qj_apply_swap(qj_handle *h, void *state, int dtype, int nqubits, int m1, int m2,
+                  const int32_t *qubits, int nactive);
+int qj_apply_fsim(qj_handle *h, void *state, int dtype, int nqubits, int m1, int m2,
+                  int swap_targets, const void *gate, const int32_t *qubits, int nactive);
+
+/* ---- k-target dense kernel (k >= 1; fused blocks use the same entry) ---------------------
+ * replaces apply_three/four/five_qubit_gate_kernel and apply_multi_qubit_gate_kernel
+ * (gates.py:266-424, raw_kernels.py:480-518; launcher gpu.py:975-1007).
+ * targets: HOST int64 single-bit masks in REVERSED target order (cpu.py:594-596):
+ * targets[u] is the index bit that matrix-index bit u addresses.                          */
+int qj_apply_multi_qubit_gate(qj_handle *h, void *state, int dtype, int nqubits,
+                              const void *gate, const int32_t *qubits, int nactive,
+                              const int64_t *targets, int ntargets);
+
+/* ---- measurement -----------------------------------------------------------------------
+ * qj_collapse_state replaces ops.collapse_state / collapse_state_normalized (ops.py:47-79),
+ * collapse_state_kernel (raw_kernels.py:521-545) + the cupy normalisation (gpu.py:640-642).
+ * qubits: HOST int32 bit positions [n-q-1 for q in reversed(sorted measured)] (cpu.py:550).  */
+int qj_collapse_state(qj_handle *h, void *state, int dtype, int nqubits, const int32_t *qubits,
+                      int ntargets, int64_t result, int normalize);
+/* squared 2-norm of the state into a host double (synchronises). */
+int qj_norm2(qj_handle *h, const void *state, int dtype, int nqubits, double *out);
+/* replaces qibo Backend.calculate_probabilities (call sites gpu.py:751-768): probs is a
+ * DEVICE array of 2^nmeas reals (float for C64, double for C128); bits[j] = index bit of the
+ * j-th measured qubit, output index has j = 0 as its most significant bit.               */
+int qj_calculate_probabilities(qj_handle *h, const void *state, int dtype, int nqubits,
+                               const int32_t *bits, int nmeas, void *probs);
+/* replaces ops.measure_frequencies (ops.py:86-108; called by cpu.py:383-394 and, on the
+ * host, by gpu.py:26,61).  frequencies: DEVICE int64[2^nqubits] (accumulated into);
+ * probs: DEVICE real[2^nqubits] (real_dtype QJ_C64 -> float, QJ_C128 -> double).
+ * Same MT19937 streams as numba: nthreads independent chains.                             */
+int qj_measure_frequencies(qj_handle *h, int64_t *frequencies, const void *probs,
+                           int real_dtype, int64_t nshots, int nqubits, int64_t seed,
+                           int nthreads);
+/* replaces qibo Backend.sample_shots (gpu.py:770-773): inverse-CDF sampling of `nshots`
+ * indices from probs (DEVICE real[2^nqubits]) with HOST uniforms u[nshots] in [0,1) drawn by
+ * the caller's generator; shots: DEVICE int64[nshots].  cdf_scratch: DEVICE double[2^nqubits]. */
+int qj_sample_shots(qj_handle *h, const void *probs, int real_dtype, int nqubits,
+                    const double *uniforms, int64_t nshots, int64_t *shots, double *cdf_scratch);
+
+/* ---- distributed state: global <-> local qubit swap ----------------------------------------
+ * replaces ops.swap_pieces (ops.py:131-137; driver loop gpu.py:1497-1507).  `local` is this
+ * rank's shard of 2^nlocal amplitudes, `peer` a pointer to the partner rank's shard that is
+ * addressable from this device (NVLink peer mapping / symmetric memory).  The rank whose
+ * global bit is 0 passes is_upper = 0.  Each rank moves half of the exchanged amplitudes:
+ * together the two calls perform piece0[i + 2^m] <-> piece1[i] for all i with bit m clear. */
+int qj_swap_pieces_peer(qj_handle *h, void *local, void *peer, int dtype, int nlocal, int m,
+                        int is_upper);
+/* Staged variant for transports without peer mapping (NCCL send/recv of chunks):
+ * pack: gather the half of `local` that leaves (bit m == 1 - is_upper) for amplitudes
+ * [chunk_begin, chunk_begin + chunk_len) of the half-shard into contiguous `buf`;
+ * unpack: scatter a received chunk into the same slots.                                    */
+int qj_swap_pack(qj_handle *h, const void *local, void *buf, int dtype, int nlocal, int m,
+                 int is_upper, int64_t chunk_begin, int64_t chunk_len);
+int qj_swap_unpack(qj_handle *h, void *local, const void *buf, int dtype, int nlocal, int m,
+                   int is_upper, int64_t chunk_begin, int64_t chunk_len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QIBOJIT_B200_H */

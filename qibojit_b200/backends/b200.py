@@ -1,0 +1,542 @@
+"""``B200Backend`` -- the reference's backend operator surface on top of the C-ABI library.
+
+Method names, argument meaning, in-place/return-the-state behaviour and error types mirror
+``NumbaBackend`` (/root/reference/src/qibojit/backends/cpu.py) and ``CupyBackend``
+(/root/reference/src/qibojit/backends/gpu.py) for the state-vector path only:
+
+* dispatch: ``GATE_OPS`` cpu.py:23-36, ``apply_gate`` :369-377, ``_apply_gate`` :433-450,
+  ``_as_custom_matrix`` :519-539, ``_create_qubits_tensor`` :565-569,
+  ``_one/_two/_multi_qubit_base`` :606-635 / :581-604, density-matrix doubling :452-517
+* state ops: ``zero_state`` :334-353, ``_collapse_statevector`` :541-563 /
+  ``collapse_state`` gpu.py:616-644, ``sample_frequencies`` cpu.py:383-394,
+  ``calculate_probabilities`` / ``sample_shots`` gpu.py:751-778
+
+States are ``torch`` CUDA tensors (torch is the device-memory / stream plumbing); every
+kernel is a call into ``libqibojit_b200.so``.  There is no CPU path: constructing the
+backend without a CUDA device raises.
+"""
+
+from collections import Counter
+
+import numpy as np
+
+from .. import _capi
+from ..matrices import CustomMatrices
+
+try:  # qibo is an un-vendored dependency of the reference; absent in this image
+    from qibo.backends import Backend as _QiboBackend  # type: ignore
+    from qibo.config import SHOT_METROPOLIS_THRESHOLD  # type: ignore
+except Exception:  # pragma: no cover - exercised whenever qibo is missing
+    _QiboBackend = object
+    SHOT_METROPOLIS_THRESHOLD = 100000  # qibo 0.3.4 config value
+
+GATE_OPS = {
+    "X": "apply_x",
+    "CNOT": "apply_x",
+    "TOFFOLI": "apply_x",
+    "Y": "apply_y",
+    "Z": "apply_z",
+    "CY": "apply_y",
+    "CZ": "apply_z",
+    "U1": "apply_z_pow",
+    "CU1": "apply_z_pow",
+    "SWAP": "apply_swap",
+    "fSim": "apply_fsim",
+    "GeneralizedfSim": "apply_fsim",
+}
+
+_DTYPE_TAG = {"complex64": _capi.QJ_C64, "complex128": _capi.QJ_C128}
+
+
+def _torch():
+    import torch  # imported lazily: keeps `import qibojit_b200` cheap on CPU-only hosts
+
+    return torch
+
+
+class B200Backend(_QiboBackend):
+    MAX_NUM_TARGETS = 10  # QJ_MAX_TARGETS (reference GPU backend: 7, gpu.py:48)
+
+    def __init__(self, device=None):
+        if _QiboBackend is not object:
+            super().__init__()
+        torch = _torch()
+        self._lib = _capi.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError(
+                "B200Backend needs a CUDA device: qibojit_b200 has no CPU fallback "
+                "(use the reference's numba backend on CPU-only hosts)."
+            )
+        import psutil
+
+        self.name = "qibojit_b200"
+        self.platform = "b200"
+        self.engine = torch
+        self.dtype = "complex128"
+        self.ngpus = torch.cuda.device_count()
+        self.supports_multigpu = True
+        self.tensor_types = (torch.Tensor, np.ndarray)
+        self.numeric_types = (int, float, complex, np.int32, np.int64, np.float32, np.float64,
+                              np.complex64, np.complex128)
+        self.custom_matrices = CustomMatrices(self.dtype)
+        self.matrices = self.custom_matrices
+        self.versions = {"qibojit_b200": self._lib.qj_version().decode(), "torch": torch.__version__}
+        self.nthreads = len(psutil.Process().cpu_affinity())
+        self._handles = {}
+        self._device_index = torch.cuda.current_device() if device is None else None
+        self.device = f"/GPU:{self._device_index}"
+        if device is not None:
+            self.set_device(device)
+
+    # ------------------------------------------------------------------ plumbing
+    def _handle(self):
+        h = self._handles.get(self._device_index)
+        if h is None:
+            torch = _torch()
+            import ctypes
+
+            out = ctypes.c_void_p()
+            stream = torch.cuda.current_stream(self._device_index).cuda_stream
+            _capi.check(self._lib.qj_create(self._device_index, ctypes.c_void_p(stream),
+                                            ctypes.byref(out)))
+            h = out
+            self._handles[self._device_index] = h
+        return h
+
+    def __del__(self):
+        try:
+            for h in self._handles.values():
+                self._lib.qj_destroy(h)
+        except Exception:
+            pass
+
+    @property
+    def torch_device(self):
+        return _torch().device("cuda", self._device_index)
+
+    def _tag(self, state):
+        tag = _DTYPE_TAG.get(str(state.dtype).replace("torch.", ""))
+        if tag is None:
+            raise TypeError(f"state dtype must be complex64 or complex128, got {state.dtype}")
+        return tag
+
+    def _np_dtype(self, state):
+        return np.complex128 if self._tag(state) == _capi.QJ_C128 else np.complex64
+
+    def _host_gate(self, gate, state):
+        """Row-major host buffer of the gate in the state dtype (gpu.py:936, 1065)."""
+        if hasattr(gate, "detach"):
+            gate = gate.detach().cpu().numpy()
+        return np.ascontiguousarray(np.asarray(gate, dtype=self._np_dtype(state)).ravel())
+
+    def synchronize(self):
+        _capi.check(self._lib.qj_sync(self._handle()))
+
+    def launch_count(self):
+        return int(self._lib.qj_launch_count(self._handle()))
+
+    def set_route(self, route):
+        """0 = automatic kernel choice, 1 = register kernels, 2 = tile kernel (tests/profiling)."""
+        _capi.check(self._lib.qj_set_route(self._handle(), int(route)))
+
+    # ------------------------------------------------------------------ setters (cpu.py:121-191)
+    def set_dtype(self, dtype):
+        dtype = str(dtype)
+        if dtype not in _DTYPE_TAG:
+            raise ValueError(f"Unsupported dtype {dtype}: use complex64 or complex128.")
+        if dtype != self.dtype:
+            self.dtype = dtype
+            self.custom_matrices = CustomMatrices(dtype)
+            self.matrices = self.custom_matrices
+
+    def set_precision(self, precision):  # older qibo spelling
+        self.set_dtype({"single": "complex64", "double": "complex128"}[precision])
+
+    def set_device(self, device):
+        torch = _torch()
+        try:
+            kind, idx = str(device).strip("/").split(":")
+            idx = int(idx)
+        except ValueError:
+            raise ValueError(f"Unknown device {device}.") from None
+        if kind.upper() != "GPU" or not 0 <= idx < torch.cuda.device_count():
+            raise ValueError(
+                f"Device {device} is not available for {self.name} ({self.platform}) backend."
+            )
+        self._device_index = idx
+        self.device = f"/GPU:{idx}"
+
+    def set_seed(self, seed):
+        np.random.seed(seed)
+
+    def set_threads(self, nthreads):
+        """Number of Metropolis chains of the high-shot sampler (cpu.py:182-191, 391-393):
+        pass the numba backend's thread count to reproduce its samples bit for bit."""
+        if not isinstance(nthreads, int) or nthreads < 1:
+            raise ValueError("nthreads must be a positive integer")
+        self.nthreads = nthreads
+
+    # ------------------------------------------------------------------ arrays
+    def cast(self, array, dtype=None, copy=False):
+        torch = _torch()
+        if dtype is None:
+            dtype = self.dtype
+        tdtype = getattr(torch, str(dtype).replace("torch.", "")) if not isinstance(dtype, torch.dtype) else dtype
+        if isinstance(array, torch.Tensor):
+            out = array.to(device=self.torch_device, dtype=tdtype)
+            return out.clone() if copy and out is array else out
+        arr = np.asarray(array)
+        return torch.as_tensor(arr, device=self.torch_device).to(tdtype)
+
+    def to_numpy(self, array):
+        if hasattr(array, "detach"):
+            return array.detach().cpu().numpy()
+        return np.asarray(array)
+
+    def assert_allclose(self, value, target, rtol=1e-7, atol=0.0):
+        np.testing.assert_allclose(self.to_numpy(value), self.to_numpy(target), rtol=rtol, atol=atol)
+
+    # ------------------------------------------------------------------ state preparation
+    def zero_state(self, nqubits, density_matrix=False, dtype=None):
+        torch = _torch()
+        if dtype is None:
+            dtype = self.dtype
+        n = 1 << nqubits
+        total_qubits = 2 * nqubits if density_matrix else nqubits
+        state = torch.empty(1 << total_qubits, dtype=getattr(torch, str(dtype)), device=self.torch_device)
+        _capi.check(self._lib.qj_initial_state(self._handle(), state.data_ptr(), self._tag(state),
+                                               total_qubits))
+        return state.reshape(n, n) if density_matrix else state
+
+    def plus_state(self, nqubits, density_matrix=False, dtype=None):
+        torch = _torch()
+        if dtype is None:
+            dtype = self.dtype
+        n = 1 << nqubits
+        tdtype = getattr(torch, str(dtype))
+        if density_matrix:
+            return torch.full((n, n), 1.0 / n, dtype=tdtype, device=self.torch_device)
+        return torch.full((n,), 1.0 / np.sqrt(n), dtype=tdtype, device=self.torch_device)
+
+    # ------------------------------------------------------------------ gate application
+    def apply_gate(self, gate, state, nqubits, inverse=False):
+        if len(state.shape) == 2:
+            return self._apply_gate_density_matrix(gate, state, nqubits, inverse)
+        return self._apply_gate(gate, state, nqubits)
+
+    def apply_gate_half_density_matrix(self, gate, state, nqubits):
+        """First half of the doubling trick only: U acting on the row index of rho
+        (qibo ``Backend.apply_gate_half_density_matrix``; pinned by the reference at
+        tests/test_gates.py:414-422)."""
+        matrix = self._as_custom_matrix(gate)
+        qubits = self._create_qubits_tensor(gate, nqubits) + nqubits
+        targets = gate.target_qubits
+        shape = state.shape
+        flat = state.reshape(-1)
+        name = gate.__class__.__name__
+        if len(targets) == 1:
+            op = GATE_OPS.get(name, "apply_gate")
+            flat = self._one_qubit_base(flat, 2 * nqubits, *targets, op, matrix, qubits)
+        elif len(targets) == 2:
+            op = GATE_OPS.get(name, "apply_two_qubit_gate")
+            flat = self._two_qubit_base(flat, 2 * nqubits, *targets, op, matrix, qubits)
+        else:
+            flat = self._multi_qubit_base(flat, 2 * nqubits, targets, matrix, qubits)
+        return flat.reshape(shape)
+
+    def apply_channel(self, channel, state, nqubits):
+        if len(state.shape) != 2:
+            raise NotImplementedError("channels on state vectors are sampled by qibo, not the backend")
+        # cpu.py:400-415
+        all_unitary = getattr(channel, "_all_unitary_operators", False)
+        state_copy = None if all_unitary else state.clone()
+        new_state = (1 - channel.coefficient_sum) * state
+        for coeff, gate in zip(channel.coefficients, channel.gates):
+            state = self.apply_gate(gate, state, nqubits)
+            new_state = new_state + coeff * state
+            if all_unitary:
+                state = self.apply_gate(gate, state, nqubits, inverse=True)
+            else:
+                state = state_copy.clone()
+        return new_state
+
+    def _apply_gate(self, gate, state, nqubits):
+        if getattr(gate, "name", None) == "fanout":
+            return self._apply_fanout_gate(gate, state, nqubits)
+        matrix = self._as_custom_matrix(gate)
+        qubits = self._create_qubits_tensor(gate, nqubits)
+        targets = gate.target_qubits
+        name = gate.__class__.__name__
+        if len(targets) == 1:
+            op = GATE_OPS.get(name, "apply_gate")
+            return self._one_qubit_base(state, nqubits, *targets, op, matrix, qubits)
+        if len(targets) == 2:
+            op = GATE_OPS.get(name, "apply_two_qubit_gate")
+            return self._two_qubit_base(state, nqubits, *targets, op, matrix, qubits)
+        return self._multi_qubit_base(state, nqubits, targets, matrix, qubits)
+
+    def _apply_fanout_gate(self, gate, state, nqubits):
+        # cpu.py:417-431: a loop of CNOTs
+        control = gate.control_qubits[0]
+        for target in gate.target_qubits:
+            qubits = np.array(sorted([nqubits - control - 1, nqubits - target - 1]), dtype=np.int32)
+            state = self._one_qubit_base(state, nqubits, target, "apply_x", None, qubits)
+        return state
+
+    def _apply_gate_density_matrix(self, gate, state, nqubits, inverse=False):
+        # cpu.py:452-498: rho flattened to a 2n-qubit vector, U on the row index then conj(U)
+        # on the column index.
+        name = gate.__class__.__name__
+        if name in ("Y", "CY"):
+            return self._apply_ygate_density_matrix(gate, state, nqubits)
+        if inverse:
+            matrix = np.linalg.inv(np.asarray(self.matrix(gate)))
+        else:
+            matrix = self._as_custom_matrix(gate)
+        qubits = self._create_qubits_tensor(gate, nqubits)
+        qubits_dm = qubits + nqubits
+        targets = gate.target_qubits
+        targets_dm = tuple(q + nqubits for q in targets)
+        shape = state.shape
+        flat = state.reshape(-1)
+        conj = None if matrix is None else np.conj(np.asarray(matrix))
+        if len(targets) == 1:
+            op = GATE_OPS.get(name, "apply_gate") if not inverse else "apply_gate"
+            flat = self._one_qubit_base(flat, 2 * nqubits, *targets, op, matrix, qubits_dm)
+            flat = self._one_qubit_base(flat, 2 * nqubits, *targets_dm, op, conj, qubits)
+        elif len(targets) == 2:
+            op = GATE_OPS.get(name, "apply_two_qubit_gate") if not inverse else "apply_two_qubit_gate"
+            flat = self._two_qubit_base(flat, 2 * nqubits, *targets, op, matrix, qubits_dm)
+            flat = self._two_qubit_base(flat, 2 * nqubits, *targets_dm, op, conj, qubits)
+        else:
+            flat = self._multi_qubit_base(flat, 2 * nqubits, targets, matrix, qubits_dm)
+            flat = self._multi_qubit_base(flat, 2 * nqubits, targets_dm, conj, qubits)
+        return flat.reshape(shape)
+
+    def _apply_ygate_density_matrix(self, gate, state, nqubits):
+        # cpu.py:500-517: the second half must use the general kernel so conj(Y) is applied
+        matrix = self._as_custom_matrix(gate)
+        qubits = self._create_qubits_tensor(gate, nqubits)
+        qubits_dm = qubits + nqubits
+        targets = gate.target_qubits
+        targets_dm = tuple(q + nqubits for q in targets)
+        shape = state.shape
+        flat = state.reshape(-1)
+        flat = self._one_qubit_base(flat, 2 * nqubits, *targets, "apply_y", matrix, qubits_dm)
+        flat = self._one_qubit_base(flat, 2 * nqubits, *targets_dm, "apply_gate", np.conj(matrix), qubits)
+        return flat.reshape(shape)
+
+    def matrix(self, gate):
+        """Full-space matrix of the gate's target part (used for channel inverses)."""
+        return self._as_custom_matrix(gate)
+
+    def matrix_fused(self, fgate):
+        """Dense matrix of a ``FusedGate`` block (qibo ``Backend.matrix_fused``, called at
+        cpu.py:535-537)."""
+        from ..fusion import fused_matrix
+
+        return fused_matrix(fgate, self.custom_matrices)
+
+    def _as_custom_matrix(self, gate):
+        # cpu.py:519-539
+        name = gate.__class__.__name__
+        if name == "FusedGate":
+            return self.matrix_fused(gate)
+        if name == "FanOut":
+            return None
+        if hasattr(gate, "target_matrix"):
+            return gate.target_matrix(self.custom_matrices)
+        _matrix = getattr(self.custom_matrices, name)
+        if getattr(gate, "parameters", ()):  # qibo ParametrizedGate
+            return _matrix(*gate.parameters)
+        return _matrix(2 ** len(gate.target_qubits)) if callable(_matrix) else _matrix
+
+    def _create_qubits_tensor(self, gate, nqubits):
+        # cpu.py:565-569
+        qubits = [nqubits - q - 1 for q in gate.control_qubits]
+        qubits.extend(nqubits - q - 1 for q in gate.target_qubits)
+        return np.array(sorted(qubits), dtype=np.int32)
+
+    @staticmethod
+    def _qubits_arg(qubits):
+        if qubits is None:
+            return None, 0
+        q = np.ascontiguousarray(np.asarray(qubits, dtype=np.int32))
+        return q, int(q.size)
+
+    def _one_qubit_base(self, state, nqubits, target, kernel, gate, qubits):
+        # cpu.py:606-616 / gpu.py:1009-1036
+        m = nqubits - target - 1
+        q, nq = self._qubits_arg(qubits)
+        qp = q.ctypes.data if q is not None else None
+        h, tag, ptr = self._handle(), self._tag(state), state.data_ptr()
+        lib = self._lib
+        if kernel == "apply_gate":
+            g = self._host_gate(gate, state)
+            rc = lib.qj_apply_gate(h, ptr, tag, nqubits, m, g.ctypes.data, qp, nq)
+        elif kernel == "apply_x":
+            rc = lib.qj_apply_x(h, ptr, tag, nqubits, m, qp, nq)
+        elif kernel == "apply_y":
+            rc = lib.qj_apply_y(h, ptr, tag, nqubits, m, qp, nq)
+        elif kernel == "apply_z":
+            rc = lib.qj_apply_z(h, ptr, tag, nqubits, m, qp, nq)
+        elif kernel == "apply_z_pow":
+            g = self._host_gate(gate, state)
+            rc = lib.qj_apply_z_pow(h, ptr, tag, nqubits, m, g.ctypes.data, qp, nq)
+        else:
+            raise ValueError(f"unknown one-qubit kernel {kernel}")
+        _capi.check(rc)
+        return state
+
+    def _two_qubit_base(self, state, nqubits, target1, target2, kernel, gate, qubits):
+        # cpu.py:618-635 / gpu.py:1038-1076
+        if target1 > target2:
+            swap_targets = 1
+            m1, m2 = nqubits - target1 - 1, nqubits - target2 - 1
+        else:
+            swap_targets = 0
+            m1, m2 = nqubits - target2 - 1, nqubits - target1 - 1
+        q, nq = self._qubits_arg(qubits)
+        qp = q.ctypes.data if q is not None else None
+        h, tag, ptr = self._handle(), self._tag(state), state.data_ptr()
+        lib = self._lib
+        if kernel == "apply_two_qubit_gate":
+            g = self._host_gate(gate, state)
+            rc = lib.qj_apply_two_qubit_gate(h, ptr, tag, nqubits, m1, m2, swap_targets,
+                                             g.ctypes.data, qp, nq)
+        elif kernel == "apply_swap":
+            rc = lib.qj_apply_swap(h, ptr, tag, nqubits, m1, m2, qp, nq)
+        elif kernel == "apply_fsim":
+            g = self._host_gate(gate, state)
+            rc = lib.qj_apply_fsim(h, ptr, tag, nqubits, m1, m2, swap_targets, g.ctypes.data, qp, nq)
+        else:
+            raise ValueError(f"unknown two-qubit kernel {kernel}")
+        _capi.check(rc)
+        return state
+
+    def _multi_qubit_base(self, state, nqubits, targets, gate, qubits):
+        # cpu.py:581-604 / gpu.py:975-1007
+        assert gate is not None
+        if qubits is None:
+            qubits = np.array(sorted(nqubits - q - 1 for q in targets), dtype=np.int32)
+        ntargets = len(targets)
+        if ntargets > self.MAX_NUM_TARGETS:
+            raise ValueError(
+                f"Number of target qubits must be <= {self.MAX_NUM_TARGETS} but is {ntargets}."
+            )
+        q, nq = self._qubits_arg(qubits)
+        tmasks = np.array([1 << (nqubits - t - 1) for t in tuple(targets)[::-1]], dtype=np.int64)
+        g = self._host_gate(gate, state)
+        _capi.check(self._lib.qj_apply_multi_qubit_gate(
+            self._handle(), state.data_ptr(), self._tag(state), nqubits, g.ctypes.data,
+            q.ctypes.data, nq, tmasks.ctypes.data, ntargets))
+        return state
+
+    # ------------------------------------------------------------------ measurement
+    def collapse_state(self, state, qubits, shot, nqubits, normalize=True, density_matrix=False):
+        if density_matrix:
+            raise NotImplementedError("density-matrix collapse is outside the state-vector path")
+        return self._collapse_statevector(state, qubits, shot, nqubits, normalize)
+
+    def _collapse_statevector(self, state, qubits, shot, nqubits, normalize=True):
+        # cpu.py:541-563
+        bits = np.array([nqubits - q - 1 for q in reversed(list(qubits))], dtype=np.int32)
+        if hasattr(shot, "detach"):
+            shot = shot.detach().cpu().numpy()
+        shot = (int(np.asarray(shot).flat[0]) if hasattr(shot, "shape") or hasattr(shot, "__len__")
+                else int(shot))
+        _capi.check(self._lib.qj_collapse_state(
+            self._handle(), state.data_ptr(), self._tag(state), nqubits,
+            bits.ctypes.data if bits.size else None, int(bits.size), shot, int(bool(normalize))))
+        return state
+
+    def calculate_norm(self, state, order=2):
+        import ctypes
+
+        if order != 2:
+            raise NotImplementedError("only the 2-norm is provided by the kernel library")
+        out = ctypes.c_double()
+        flat = state.reshape(-1)
+        nq = int(flat.numel()).bit_length() - 1
+        _capi.check(self._lib.qj_norm2(self._handle(), flat.data_ptr(), self._tag(flat), nq,
+                                       ctypes.byref(out)))
+        return float(np.sqrt(out.value))
+
+    def calculate_probabilities(self, state, qubits, nqubits, density_matrix=False):
+        torch = _torch()
+        if density_matrix:
+            raise NotImplementedError("density-matrix probabilities are outside the state-vector path")
+        qubits = list(qubits)
+        bits = np.array([nqubits - q - 1 for q in qubits], dtype=np.int32)
+        rdtype = torch.float64 if self._tag(state) == _capi.QJ_C128 else torch.float32
+        probs = torch.empty(1 << len(qubits), dtype=rdtype, device=state.device)
+        _capi.check(self._lib.qj_calculate_probabilities(
+            self._handle(), state.data_ptr(), self._tag(state), nqubits,
+            bits.ctypes.data if bits.size else None, int(bits.size), probs.data_ptr()))
+        return probs
+
+    def _real_tag(self, probs):
+        torch = _torch()
+        if probs.dtype == torch.float64:
+            return _capi.QJ_C128
+        if probs.dtype == torch.float32:
+            return _capi.QJ_C64
+        raise TypeError("probabilities must be float32 or float64")
+
+    def sample_shots(self, probabilities, nshots):
+        """Inverse-CDF sampling on the device with uniforms from the host generator that
+        ``set_seed`` seeds (numpy legacy ``RandomState``, as ``np.random.choice(p=...)`` uses)."""
+        torch = _torch()
+        probs = self.cast(probabilities, dtype=probabilities.dtype if hasattr(probabilities, "dtype") and str(probabilities.dtype).replace("torch.", "") in ("float32", "float64") else "float64")
+        nq = int(probs.numel()).bit_length() - 1
+        uniforms = np.ascontiguousarray(np.random.random_sample(int(nshots)))
+        shots = torch.empty(int(nshots), dtype=torch.int64, device=probs.device)
+        cdf = torch.empty(probs.numel(), dtype=torch.float64, device=probs.device)
+        _capi.check(self._lib.qj_sample_shots(
+            self._handle(), probs.data_ptr(), self._real_tag(probs), nq, uniforms.ctypes.data,
+            int(nshots), shots.data_ptr(), cdf.data_ptr()))
+        return shots
+
+    def calculate_frequencies(self, samples):
+        torch = _torch()
+        samples = samples if hasattr(samples, "detach") else torch.as_tensor(np.asarray(samples))
+        res, counts = torch.unique(samples, return_counts=True)
+        return Counter(dict(zip(res.cpu().tolist(), counts.cpu().tolist())))
+
+    def sample_frequencies(self, probabilities, nshots):
+        # cpu.py:383-394
+        torch = _torch()
+        if nshots < SHOT_METROPOLIS_THRESHOLD:
+            return self.calculate_frequencies(self.sample_shots(probabilities, nshots))
+        seed = int(np.random.randint(0, int(1e8), size=1, dtype=np.int64)[0])
+        probs = probabilities if hasattr(probabilities, "detach") else self.cast(probabilities, dtype=str(np.asarray(probabilities).dtype))
+        nq = int(probs.numel()).bit_length() - 1
+        freqs = torch.zeros(probs.numel(), dtype=torch.int64, device=probs.device)
+        self.measure_frequencies_op(freqs, probs, nshots, nq, seed, self.nthreads)
+        nz = torch.nonzero(freqs).reshape(-1)
+        return Counter(dict(zip(nz.cpu().tolist(), freqs[nz].cpu().tolist())))
+
+    def measure_frequencies_op(self, frequencies, probs, nshots, nqubits, seed, nthreads):
+        """ops.measure_frequencies (ops.py:86-108) on device tensors."""
+        _capi.check(self._lib.qj_measure_frequencies(
+            self._handle(), frequencies.data_ptr(), probs.data_ptr(), self._real_tag(probs),
+            int(nshots), int(nqubits), int(seed), int(nthreads)))
+        return frequencies
+
+    # ------------------------------------------------------------------ circuits
+    def execute_circuit(self, circuit, initial_state=None, nshots=None):
+        """Minimal stand-in for qibo's ``Backend.execute_circuit``:
+        zero state (or a cast copy of `initial_state`), then every gate of ``circuit.queue``."""
+        nqubits = circuit.nqubits
+        if initial_state is None:
+            state = self.zero_state(nqubits)
+        else:
+            state = self.cast(initial_state, copy=True)
+        for gate in circuit.queue:
+            state = gate.apply(self, state, nqubits)
+        return state
+
+    def execute_distributed_circuit(self, circuit, initial_state=None, nshots=None):
+        from ..distributed import execute_distributed_circuit
+
+        return execute_distributed_circuit(self, circuit, initial_state, nshots)
