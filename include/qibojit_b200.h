@@ -45,8 +45,8 @@ extern "C" {
 typedef struct qj_handle qj_handle;
 
 /* ---- handle / runtime ------------------------------------------------------------ */
-/* stream: a cudaStream_t created by the caller (e.g. torch's current stream) or NULL to let
- * the handle own a private non-blocking stream. */
+/* stream: the cudaStream_t every call of this handle is enqueued on (e.g. torch's current
+ * stream); NULL is the CUDA default stream. */
 int qj_create(int device, void *stream, qj_handle **out);
 int qj_destroy(qj_handle *h);
 int qj_set_stream(qj_handle *h, void *stream);

@@ -148,12 +148,9 @@ int qj_create(int device, void *stream, qj_handle **out) {
     cudaDeviceProp prop;
     QJ_CUDA_OK(cudaGetDeviceProperties(&prop, device));
     h->sm_count = prop.multiProcessorCount;
-    if (stream) {
-        h->stream = static_cast<cudaStream_t>(stream);
-    } else {
-        QJ_CUDA_OK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-        h->own_stream = true;
-    }
+    // NULL is the CUDA default stream -- what torch uses unless told otherwise -- so work
+    // enqueued here is ordered with the caller's copies and reads of the state.
+    h->stream = static_cast<cudaStream_t>(stream);
     h->scratch_doubles = size_t(2) << 20;  // 16 MiB
     QJ_CUDA_OK(cudaMalloc(&h->scratch, h->scratch_doubles * sizeof(double)));
     h->gate_slots = 4;

@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 GATE_CASES = list(goldenio.iter_gate_cases(cases, R))
 
 
-@pytest.mark.parametrize("route", [1, 0], ids=["direct", "auto"])
+@pytest.mark.parametrize("route", [1, 0, 2], ids=["direct", "auto", "tile"])
 @pytest.mark.parametrize("case", GATE_CASES, ids=[c[0] for c in GATE_CASES])
 def test_gate_kernels_match_reference_golden(case, route, golden_gates):
     key, kind, dtype, nq, t, c, seed = case
@@ -84,9 +84,10 @@ def test_too_many_targets_raises():
         b._multi_qubit_base(st, n, list(range(11)), np.eye(2 ** 11), None)
 
 
+@pytest.mark.parametrize("route", [1, 2], ids=["direct", "tile"])
 @pytest.mark.parametrize("dtype", cases.DTYPES)
 @pytest.mark.parametrize("nqubits", [18, 22])
-def test_every_target_bit_vs_oracle(nqubits, dtype):
+def test_every_target_bit_vs_oracle(nqubits, dtype, route):
     """Sweep the target over every index bit (all access regimes of the kernels)."""
     b = backend()
     from oracle import oracle as O
@@ -94,11 +95,50 @@ def test_every_target_bit_vs_oracle(nqubits, dtype):
     st = R.random_state(nqubits, dtype, 9)
     d = b.cast(st, dtype=dtype, copy=True)
     ref = st.copy()
-    for target in range(nqubits):
-        m = R.random_matrix(2, dtype, target)
-        m = m / np.linalg.norm(m, 2)
-        d = b._one_qubit_base(d, nqubits, target, "apply_gate", m, None)
-        ref = R.one_qubit_base(O, ref, nqubits, target, "apply_gate", m, None)
+    b.set_route(route)
+    try:
+        for target in range(nqubits):
+            m = R.random_matrix(2, dtype, target)
+            m = m / np.linalg.norm(m, 2)
+            d = b._one_qubit_base(d, nqubits, target, "apply_gate", m, None)
+            ref = R.one_qubit_base(O, ref, nqubits, target, "apply_gate", m, None)
+    finally:
+        b.set_route(0)
+    b.assert_allclose(d, ref, rtol=0, atol=ATOL[dtype])
+
+
+@pytest.mark.parametrize("route", [1, 2], ids=["direct", "tile"])
+@pytest.mark.parametrize("dtype", cases.DTYPES)
+@pytest.mark.parametrize("k", [2, 3, 4, 5])
+def test_random_target_sets_vs_oracle(k, dtype, route):
+    """Dense k-target gates on random (unsorted) target sets with random controls, n = 20:
+    low, mixed and high bit positions; the fused-block kernel's whole geometry space."""
+    b = backend()
+    from oracle import oracle as O
+
+    n = 20
+    rng = np.random.default_rng(100 + k)
+    st = R.random_state(n, dtype, 13)
+    d = b.cast(st, dtype=dtype, copy=True)
+    ref = st.copy()
+    b.set_route(route)
+    try:
+        for trial in range(8):
+            qs = [int(v) for v in rng.permutation(n)[: k + (trial % 3)]]
+            targets, controls = qs[:k], qs[k:]
+            if trial == 0:
+                targets = list(range(n - k, n))          # the k lowest index bits
+                controls = []
+            if trial == 1:
+                targets = list(range(k))[::-1]            # the k highest index bits, reversed
+                controls = [n - 1]
+            m = R.random_matrix(1 << k, dtype, trial)
+            m = m / np.linalg.norm(m, 2)
+            q = R.qubits_tensor(n, targets, controls)
+            d = b._multi_qubit_base(d, n, targets, m, q)
+            ref = R.multi_qubit_base(O, ref, n, targets, m, q)
+    finally:
+        b.set_route(0)
     b.assert_allclose(d, ref, rtol=0, atol=ATOL[dtype])
 
 
