@@ -25,7 +25,7 @@
 namespace qj {
 namespace {
 
-constexpr int kTileThreads = 256;
+constexpr int kTileThreads = 128;
 constexpr int kStages = 4;
 
 struct TileGeom {
@@ -97,7 +97,34 @@ __device__ __forceinline__ int64_t tile_base(int64_t tile, const TileGeom &tg) {
     return (g | tg.cmask) << tg.r;
 }
 
-template <typename T, int K>
+// rows [S*RPT, (S+1)*RPT) of the tuple: fully unrolled so every matrix element is an
+// immediate constant-bank operand of its FMA
+template <typename T, int K, int SL, int S>
+__device__ __forceinline__ void tile_rows(const Cx<T> (&x)[1 << K], Cx<T> *__restrict__ tile, int lb,
+                                          const TileGeom &tg, const CMat<T, (1 << K)> &mat) {
+    constexpr int NE = 1 << K;
+    constexpr int RPT = NE >> SL;
+#pragma unroll
+    for (int ii = 0; ii < RPT; ii++) {
+        constexpr int dummy = 0;
+        (void)dummy;
+        const int i = S * RPT + ii;
+        T ar = T(0), ai = T(0);
+#pragma unroll
+        for (int j = 0; j < NE; j++) {
+            const T gr = mat.v[2 * (i * NE + j)], gi = mat.v[2 * (i * NE + j) + 1];
+            ar = fma(gr, x[j].re, ar);
+            ar = fma(-gi, x[j].im, ar);
+            ai = fma(gr, x[j].im, ai);
+            ai = fma(gi, x[j].re, ai);
+        }
+        Cx<T> y; y.re = ar; y.im = ai;
+        tile[lb + tg.loff[i]] = y;
+    }
+}
+
+// SL = log2 of the row slices a tuple is split into (slice index is warp-uniform)
+template <typename T, int K, int SL>
 __global__ void __launch_bounds__(kTileThreads)
 k_dense_tile(Cx<T> *__restrict__ state, const __grid_constant__ TileGeom tg,
              const __grid_constant__ CMat<T, (1 << K)> mat) {
@@ -109,7 +136,7 @@ k_dense_tile(Cx<T> *__restrict__ state, const __grid_constant__ TileGeom tg,
     const int tile_amps = 1 << tg.T;
     const uint32_t run_bytes = uint32_t(sizeof(Cx<T>)) << tg.r;
     const uint32_t tile_bytes = uint32_t(sizeof(Cx<T>)) << tg.T;
-    const int nruns = 1 << tg.nh;
+    const int nruns = 1 << tg.nh;  // <= 32: lane h of warp 0 moves run h
     Cx<T> *bufs = reinterpret_cast<Cx<T> *>(smem_raw);
 
     if (tid == 0) {
@@ -123,27 +150,24 @@ k_dense_tile(Cx<T> *__restrict__ state, const __grid_constant__ TileGeom tg,
     const int64_t step = gridDim.x;
     const int64_t my_count = (tg.ntiles > first) ? (tg.ntiles - first + step - 1) / step : 0;
 
-    // warp 0 moves the data: lane l issues the copies of runs l, l + 32, ...
+    // warp 0 moves the data; the run a lane owns is fixed for the whole kernel
+    int64_t my_goff = 0;
+    for (int b = 0; b < tg.nh; b++) my_goff |= int64_t((tid >> b) & 1) << tg.hibit[b];
+    const size_t my_soff = size_t(tid & 31) << tg.r;
+    const bool mover = tid < nruns;
+
     auto issue_load = [&](int64_t it) {
         const int s = int(it % kStages);
         const int64_t base = tile_base(first + it * step, tg);
         if (tid == 0) mbar_expect_tx(&full_bar[s], tile_bytes);
         __syncwarp();
-        for (int h = tid; h < nruns; h += 32) {
-            int64_t off = 0;
-            for (int b = 0; b < tg.nh; b++) off |= int64_t((h >> b) & 1) << tg.hibit[b];
-            bulk_g2s(bufs + size_t(s) * tile_amps + (size_t(h) << tg.r), state + base + off, run_bytes,
-                     &full_bar[s]);
-        }
+        if (mover)
+            bulk_g2s(bufs + size_t(s) * tile_amps + my_soff, state + base + my_goff, run_bytes, &full_bar[s]);
     };
     auto issue_store = [&](int64_t it) {
         const int s = int(it % kStages);
         const int64_t base = tile_base(first + it * step, tg);
-        for (int h = tid; h < nruns; h += 32) {
-            int64_t off = 0;
-            for (int b = 0; b < tg.nh; b++) off |= int64_t((h >> b) & 1) << tg.hibit[b];
-            bulk_s2g(state + base + off, bufs + size_t(s) * tile_amps + (size_t(h) << tg.r), run_bytes);
-        }
+        if (mover) bulk_s2g(state + base + my_goff, bufs + size_t(s) * tile_amps + my_soff, run_bytes);
         bulk_commit();
     };
 
@@ -151,13 +175,12 @@ k_dense_tile(Cx<T> *__restrict__ state, const __grid_constant__ TileGeom tg,
         for (int64_t it = 0; it < kStages - 2 && it < my_count; it++) issue_load(it);
     }
 
-    // compute-phase geometry
+    // compute-phase geometry: 2^(T-K) tuples, each split into 2^SL row slices
+    constexpr int kThreadsLog = 7;
     const int ntuples_log = tg.T - K;
-    const int ntuples = 1 << ntuples_log;
-    const int split_log = (ntuples_log >= 8) ? 0 : (8 - ntuples_log);  // 256 threads
-    const int rows_per_thread = NE >> split_log;
-    const int rounds = (ntuples_log > 8) ? (1 << (ntuples_log - 8)) : 1;
-    const int slice = tid >> ((ntuples_log < 8) ? ntuples_log : 8);
+    const int rounds = (ntuples_log + SL > kThreadsLog) ? (1 << (ntuples_log + SL - kThreadsLog)) : 1;
+    const int slice = (SL == 0) ? 0 : (tid >> (kThreadsLog - SL));
+    const int tuple_lane = (SL == 0) ? tid : (tid & ((1 << (kThreadsLog - SL)) - 1));
 
     for (int64_t it = 0; it < my_count; it++) {
         const int s = int(it % kStages);
@@ -176,7 +199,7 @@ k_dense_tile(Cx<T> *__restrict__ state, const __grid_constant__ TileGeom tg,
 
         for (int rd = 0; rd < rounds; rd++) {
             // local base: insert zeros at the target positions
-            int lb = (ntuples_log >= 8) ? ((rd << 8) | tid) : (tid & (ntuples - 1));
+            int lb = (rd << (kThreadsLog - SL)) | tuple_lane;
 #pragma unroll
             for (int j = 0; j < K; j++) {
                 const int p = tg.tpos[j];
@@ -188,24 +211,23 @@ k_dense_tile(Cx<T> *__restrict__ state, const __grid_constant__ TileGeom tg,
 #pragma unroll
                 for (int e = 0; e < NE; e++) x[e] = tile[lb + tg.loff[e]];
             }
-            if (split_log > 0) __syncthreads();
+            if (SL > 0) __syncthreads();
             if (active) {
-#pragma unroll 1
-                for (int ii = 0; ii < rows_per_thread; ii++) {
-                    const int i = slice * rows_per_thread + ii;
-                    T ar = T(0), ai = T(0);
-#pragma unroll
-                    for (int j = 0; j < NE; j++) {
-                        const T gr = mat.v[2 * (i * NE + j)], gi = mat.v[2 * (i * NE + j) + 1];
-                        ar = fma(gr, x[j].re, ar);
-                        ar = fma(-gi, x[j].im, ar);
-                        ai = fma(gr, x[j].im, ai);
-                        ai = fma(gi, x[j].re, ai);
+                if (SL == 0) {
+                    tile_rows<T, K, 0, 0>(x, tile, lb, tg, mat);
+                } else if (SL == 1) {
+                    if (slice == 0) tile_rows<T, K, SL, 0>(x, tile, lb, tg, mat);
+                    else tile_rows<T, K, SL, (SL >= 1 ? 1 : 0)>(x, tile, lb, tg, mat);
+                } else {
+                    switch (slice) {
+                        case 0: tile_rows<T, K, SL, 0>(x, tile, lb, tg, mat); break;
+                        case 1: tile_rows<T, K, SL, (SL >= 2 ? 1 : 0)>(x, tile, lb, tg, mat); break;
+                        case 2: tile_rows<T, K, SL, (SL >= 2 ? 2 : 0)>(x, tile, lb, tg, mat); break;
+                        default: tile_rows<T, K, SL, (SL >= 2 ? 3 : 0)>(x, tile, lb, tg, mat); break;
                     }
-                    Cx<T> y; y.re = ar; y.im = ai;
-                    tile[lb + tg.loff[i]] = y;
                 }
             }
+            if (SL > 0 && rounds > 1) __syncthreads();
         }
         fence_async_smem();
         __syncthreads();
@@ -296,24 +318,39 @@ bool plan_tile(const qj_handle *h, const GateCall &c, TilePlan *out) {
     return true;
 }
 
-template <typename T, int K>
-int launch_tile_k(qj_handle *h, const GateCall &c, const TilePlan &p) {
+template <typename T, int K, int SL>
+int launch_tile_ks(qj_handle *h, const GateCall &c, const TilePlan &p) {
     constexpr int NE = 1 << K;
     CMat<T, NE> mat;
     memcpy(mat.v, c.gate, sizeof(mat.v));
     static bool configured = false;
+    static int per_sm_cached[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (!configured) {
-        QJ_CUDA_OK(cudaFuncSetAttribute(k_dense_tile<T, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 << 10));
+        QJ_CUDA_OK(cudaFuncSetAttribute(k_dense_tile<T, K, SL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 << 10));
         configured = true;
     }
-    int per_sm = 1;
-    QJ_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_dense_tile<T, K>, kTileThreads, p.smem));
-    per_sm = std::max(1, per_sm);
-    const unsigned grid = (unsigned)std::min<int64_t>(p.tg.ntiles, int64_t(h->sm_count) * per_sm);
-    k_dense_tile<T, K><<<grid, kTileThreads, p.smem, h->stream>>>(reinterpret_cast<Cx<T> *>(c.state), p.tg, mat);
+    const int slot = std::min<int>(7, int(p.smem >> 15));
+    if (per_sm_cached[slot] == 0) {
+        int per_sm = 1;
+        QJ_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_dense_tile<T, K, SL>, kTileThreads, p.smem));
+        per_sm_cached[slot] = std::max(1, per_sm);
+    }
+    const unsigned grid = (unsigned)std::min<int64_t>(p.tg.ntiles, int64_t(h->sm_count) * per_sm_cached[slot]);
+    k_dense_tile<T, K, SL><<<grid, kTileThreads, p.smem, h->stream>>>(reinterpret_cast<Cx<T> *>(c.state), p.tg, mat);
     h->launches++;
     QJ_CUDA_OK(cudaGetLastError());
     return QJ_OK;
+}
+
+// slices needed so that 2^(T-K) tuples x 2^SL slices cover the 128 threads of a CTA
+template <typename T, int K>
+int launch_tile_k(qj_handle *h, const GateCall &c, const TilePlan &p) {
+    const int sl = std::max(0, 7 - (p.tg.T - K));
+    if (sl > 2 || sl > K) return fail(QJ_ERR_UNSUPPORTED, "tile too small for the tile kernel");
+    if (sl == 0) return launch_tile_ks<T, K, 0>(h, c, p);
+    if constexpr (K >= 1) { if (sl == 1) return launch_tile_ks<T, K, 1>(h, c, p); }
+    if constexpr (K >= 2) { if (sl == 2) return launch_tile_ks<T, K, 2>(h, c, p); }
+    return fail(QJ_ERR_UNSUPPORTED, "tile kernel slice configuration");
 }
 
 template <typename T>
