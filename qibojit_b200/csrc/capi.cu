@@ -76,13 +76,9 @@ int route_dense(qj_handle *h, const GateCall &c) {
         return launch_dense_generic(h, c);
     }
     if (h->route == 2 && tile_kernel_applies(h, c)) return launch_dense_tile(h, c);
-    if (h->route == 0 && tile_kernel_applies(h, c)) {
-        // automatic: the tile kernel wins when a target sits on the low index bits (strided
-        // 16-byte accesses in the direct kernel) or the tuple is large (k >= 4)
-        bool low = false;
-        for (int u = 0; u < c.ntargets; u++) low |= (c.tbits[u] < 3);
-        if (low || c.ntargets >= 4) return launch_dense_tile(h, c);
-    }
+    // automatic: measured on B200 (profiles/sweep_*.json) the register kernels are at or above
+    // the copy-bandwidth roofline for k <= 4 wherever the targets sit, so they are the default;
+    // the tile kernel stays selectable (route 2) for comparison and profiling.
     return launch_dense_direct(h, c);
 }
 

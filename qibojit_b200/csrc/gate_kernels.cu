@@ -51,7 +51,7 @@ k_dense_direct(typename VecOf<T, V>::type *__restrict__ st, const __grid_constan
 #pragma unroll
     for (int u = 0; u < U; u++) {
         if (base[u] < 0) continue;
-#pragma unroll(K <= 3 ? NE : 1)
+#pragma unroll
         for (int i = 0; i < NE; i++) {
             Amp<T, V> acc;
 #pragma unroll
