@@ -79,6 +79,12 @@ int qj_apply_z(qj_handle *h, void *state, int dtype, int nqubits, int m,
 int qj_apply_z_pow(qj_handle *h, void *state, int dtype, int nqubits, int m, const void *phase,
                    const int32_t *qubits, int nactive);
 
+/* multiply every amplitude by one complex scalar (HOST pointer, state dtype): the form a
+ * diagonal gate takes on a shard whose rank bits fix all of its qubits (distributed rule iii;
+ * no single reference kernel -- the reference rebuilds the full vector on the host for such
+ * gates, gpu.py:1478-1495). */
+int qj_apply_phase(qj_handle *h, void *state, int dtype, int nqubits, const void *phase);
+
 /* ---- two-target kernels --------------------------------------------------------------
  * replace {,multicontrol_}apply_two_qubit_gate / apply_swap / apply_fsim
  * (gates.py:118-254, raw_kernels.py:224-290 and 394-477; launcher gpu.py:1038-1076).

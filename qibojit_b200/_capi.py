@@ -33,6 +33,7 @@ SIGNATURES = {
     "qj_apply_y": (_I, [_P, _P, _I, _I, _I, _P, _I]),
     "qj_apply_z": (_I, [_P, _P, _I, _I, _I, _P, _I]),
     "qj_apply_z_pow": (_I, [_P, _P, _I, _I, _I, _P, _P, _I]),
+    "qj_apply_phase": (_I, [_P, _P, _I, _I, _P]),
     "qj_apply_two_qubit_gate": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _I]),
     "qj_apply_swap": (_I, [_P, _P, _I, _I, _I, _I, _P, _I]),
     "qj_apply_fsim": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _I]),

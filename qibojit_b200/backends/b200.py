@@ -523,6 +523,71 @@ class B200Backend(_QiboBackend):
             int(nshots), int(nqubits), int(seed), int(nthreads)))
         return frequencies
 
+    # ------------------------------------------------------------------ shard primitives
+    # (used by qibojit_b200.distributed; the reference keeps pieces in host RAM and swaps them
+    #  with ops.swap_pieces on the CPU, gpu.py:1497-1507)
+    def shard_zeros(self, nlocal, dtype, one_at_zero=False):
+        torch = _torch()
+        if one_at_zero:
+            return self.zero_state(nlocal, dtype=dtype)
+        return torch.zeros(1 << nlocal, dtype=getattr(torch, str(dtype)), device=self.torch_device)
+
+    def shard_scale(self, shard, nlocal, phase):
+        ph = np.asarray(phase, dtype=self._np_dtype(shard)).reshape(1)
+        _capi.check(self._lib.qj_apply_phase(self._handle(), shard.data_ptr(), self._tag(shard),
+                                             nlocal, ph.ctypes.data))
+        return shard
+
+    def _staging(self, nelem, dtype, which):
+        torch = _torch()
+        key = (which, dtype)
+        buf = getattr(self, "_stage_bufs", {}).get(key)
+        if buf is None or buf.numel() < nelem:
+            if not hasattr(self, "_stage_bufs"):
+                self._stage_bufs = {}
+            buf = torch.empty(nelem, dtype=dtype, device=self.torch_device)
+            self._stage_bufs[key] = buf
+        return buf[:nelem]
+
+    def shard_exchange(self, shard, nlocal, lbit, peer, is_upper, comm, chunk_bytes=1 << 29):
+        """Global<->local qubit swap with rank `peer` (ops.swap_pieces semantics): the amplitudes
+        of this shard whose local bit `lbit` equals (1 - is_upper) are exchanged with the peer's
+        complementary half, chunk by chunk through a small staging buffer (nothing state-sized is
+        allocated).  When `lbit` is the top local bit both halves are contiguous and travel
+        straight from / into the shard; otherwise they are packed / unpacked by the library's
+        strided-copy kernels.  Returns the bytes sent."""
+        dist = comm.dist
+        half = 1 << (nlocal - 1)
+        esize = shard.element_size()
+        chunk = max(2, min(half, chunk_bytes // esize))
+        contiguous = lbit == nlocal - 1
+        tag = self._tag(shard)
+        h = self._handle()
+        region = None
+        if contiguous:
+            region = shard[:half] if is_upper else shard[half:]
+        for c0 in range(0, half, chunk):
+            n = min(chunk, half - c0)
+            recv = self._staging(n, shard.dtype, "recv")
+            if contiguous:
+                send = region[c0:c0 + n]
+            else:
+                send = self._staging(n, shard.dtype, "send")
+                _capi.check(self._lib.qj_swap_pack(h, shard.data_ptr(), send.data_ptr(), tag, nlocal,
+                                                   lbit, int(is_upper), c0, n))
+            # NCCL moves real pairs; the complex views share storage
+            torch = _torch()
+            ops = [dist.P2POp(dist.isend, torch.view_as_real(send), peer, group=comm.group),
+                   dist.P2POp(dist.irecv, torch.view_as_real(recv), peer, group=comm.group)]
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+            if contiguous:
+                region[c0:c0 + n].copy_(recv)
+            else:
+                _capi.check(self._lib.qj_swap_unpack(h, shard.data_ptr(), recv.data_ptr(), tag, nlocal,
+                                                     lbit, int(is_upper), c0, n))
+        return half * esize
+
     # ------------------------------------------------------------------ circuits
     def execute_circuit(self, circuit, initial_state=None, nshots=None):
         """Minimal stand-in for qibo's ``Backend.execute_circuit``:

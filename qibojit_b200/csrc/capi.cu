@@ -216,6 +216,16 @@ int qj_apply_z_pow(qj_handle *h, void *state, int dtype, int nqubits, int m, con
     return one_target(h, state, dtype, nqubits, m, phase, qubits, nactive, OP_ZPOW);
 }
 
+int qj_apply_phase(qj_handle *h, void *state, int dtype, int nqubits, const void *phase) {
+    int rc = check_common(h, state, dtype, nqubits);
+    if (rc) return rc;
+    QJ_REQUIRE(phase != nullptr, "null phase");
+    GateCall c;
+    memset(&c, 0, sizeof(c));
+    c.state = state; c.dtype = dtype; c.nqubits = nqubits; c.ntargets = 0; c.gate = phase;
+    return launch_special(h, c, OP_PHASE);
+}
+
 int qj_apply_two_qubit_gate(qj_handle *h, void *state, int dtype, int nqubits, int m1, int m2,
                             int swap_targets, const void *gate, const int32_t *qubits, int nactive) {
     return two_target(h, state, dtype, nqubits, m1, m2, swap_targets, gate, qubits, nactive, 0);

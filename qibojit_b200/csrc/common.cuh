@@ -172,7 +172,7 @@ struct GateCall {
     const void *gate;            // host, row-major 2^k x 2^k in the state dtype (may be null)
 };
 
-enum SpecialOp { OP_X = 1, OP_Y = 2, OP_Z = 3, OP_ZPOW = 4, OP_SWAP = 5, OP_FSIM = 6 };
+enum SpecialOp { OP_X = 1, OP_Y = 2, OP_Z = 3, OP_ZPOW = 4, OP_SWAP = 5, OP_FSIM = 6, OP_PHASE = 7 };
 
 int launch_dense_direct(qj_handle *h, const GateCall &c);
 int launch_special(qj_handle *h, const GateCall &c, int op);

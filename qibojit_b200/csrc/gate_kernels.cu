@@ -299,7 +299,9 @@ int launch_dense_tv(qj_handle *h, const GateCall &c, const Plan &p) {
 
 int launch_dense_direct(qj_handle *h, const GateCall &c) {
     Plan p;
-    int rc = make_plan(c, c.ntargets, c.tbits, c.cbits, c.ncontrols, true, &p);
+    // complex64, k = 5: the two-amplitude vector form needs ~170 registers and runs at half the
+    // speed of the scalar form (measured, profiles/sweep_c64): keep one amplitude per access
+    int rc = make_plan(c, c.ntargets, c.tbits, c.cbits, c.ncontrols, c.ntargets < 5, &p);
     if (rc) return rc;
     for (int e = 0; e < (1 << c.ntargets); e++) {
         int64_t o = 0;
@@ -335,6 +337,7 @@ int launch_special_tv(qj_handle *h, const GateCall &c, const Plan &p, int op) {
             return launch_checked(h, [&] {
                 k_diag1<T, V, U, true><<<grid, kThreads, 0, h->stream>>>(st, p.geo, T(0), T(0));
             });
+        case OP_PHASE:
         case OP_ZPOW:
             return launch_checked(h, [&] {
                 k_diag1<T, V, U, false><<<grid, kThreads, 0, h->stream>>>(st, p.geo, g[0], g[1]);
@@ -356,10 +359,10 @@ int launch_special(qj_handle *h, const GateCall &c, int op) {
     Plan p;
     int rc;
     std::vector<int> fixed(c.cbits, c.cbits + c.ncontrols);
-    if (op == OP_Z || op == OP_ZPOW) {
+    if (op == OP_Z || op == OP_ZPOW || op == OP_PHASE) {
         // diagonal: target bit behaves like one more control; the single touched element
-        // sits at offset 0 from the (controls | target) base
-        fixed.push_back(c.tbits[0]);
+        // sits at offset 0 from the (controls | target) base.  OP_PHASE has no qubits at all.
+        if (op != OP_PHASE) fixed.push_back(c.tbits[0]);
         rc = make_plan(c, 0, nullptr, fixed.data(), (int)fixed.size(), true, &p);
         if (rc) return rc;
         p.geo.off[0] = 0;

@@ -1,0 +1,327 @@
+"""Distributed state layer: the top log2(G) index bits are sharded over G ranks (one process
+per GPU, ``torch.distributed``), non-diagonal gates on a sharded ("global") qubit trigger a
+global<->local qubit swap.
+
+What it replaces: ``CupyBackend.execute_distributed_circuit`` and ``MultiGpuOps``
+(/root/reference/src/qibojit/backends/gpu.py:646-739, 1420-1516), where the pieces live in host
+RAM, each gate group costs a host<->device round trip per piece and global swaps run on the CPU
+(``ops.swap_pieces``, ops.py:131-137).  Here the shards stay resident in HBM and only half a
+shard crosses NVLink per swap.  The piece layout is the reference's for global qubits
+``[0..g-1]`` (gpu.py:1440-1442): rank r holds amplitudes ``[r * 2^nlocal, (r+1) * 2^nlocal)``.
+
+Rules:
+  (i)   gate on local bits only          -> every rank runs the local kernel
+  (ii)  control on a global qubit        -> only ranks whose bit is 1 run it, control dropped
+  (iii) diagonal gate on a global target -> restricted to the rank's bit value: a smaller local
+        diagonal gate or a scalar phase on the shard; no exchange
+  (iv)  anything else                    -> swap the global qubit with a local one first
+        (``swap_pieces`` semantics), choosing the local qubit whose next use is farthest away
+  SWAP gates are executed by relabelling the qubit map (no data movement at all).
+
+The class talks to the device only through the backend's reference-style kernel entry points
+(``_one_qubit_base`` ...) plus three shard primitives of the backend (``shard_zeros``,
+``shard_scale``, ``shard_exchange``), so the same logic runs on gloo/CPU in the tests with a
+numpy stand-in backend.
+"""
+
+import numpy as np
+
+from .backends.b200 import GATE_OPS  # noqa: F401  (re-exported for stand-in backends)
+
+_SYMMETRIC_PHASE_OPS = ("apply_z", "apply_z_pow")
+
+
+def _log2(x):
+    n = int(x).bit_length() - 1
+    if (1 << n) != x:
+        raise ValueError(f"{x} is not a power of two")
+    return n
+
+
+class Comm:
+    """Thin view of a torch.distributed process group (or a single-rank stub)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+
+        self.dist = dist
+        self.group = group
+        if dist.is_available() and dist.is_initialized():
+            self.rank = dist.get_rank(group)
+            self.world = dist.get_world_size(group)
+        else:
+            self.rank, self.world = 0, 1
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier(group=self.group)
+
+    def all_reduce_sum(self, tensor):
+        if self.world > 1:
+            self.dist.all_reduce(tensor, op=self.dist.ReduceOp.SUM, group=self.group)
+        return tensor
+
+    def all_gather(self, tensor):
+        if self.world == 1:
+            return [tensor]
+        import torch
+
+        out = [torch.empty_like(tensor) for _ in range(self.world)]
+        self.dist.all_gather(out, tensor, group=self.group)
+        return out
+
+
+def is_diagonal_matrix(m, tol=0.0):
+    m = np.asarray(m)
+    if m.ndim != 2:
+        return False
+    off = m - np.diag(np.diagonal(m))
+    return bool(np.all(np.abs(off) <= tol))
+
+
+class DistributedState:
+    """A 2^nqubits state vector sharded over the ranks of `comm`."""
+
+    def __init__(self, backend, nqubits, comm=None, dtype=None, swap_chunk_bytes=1 << 29):
+        self.backend = backend
+        self.comm = comm if comm is not None else Comm()
+        self.nqubits = int(nqubits)
+        self.nglobal = _log2(self.comm.world)
+        self.nlocal = self.nqubits - self.nglobal
+        if self.nlocal < 1:
+            raise ValueError("more ranks than amplitudes pairs: use fewer devices")
+        self.dtype = dtype or backend.dtype
+        self.rank = self.comm.rank
+        # logical qubit -> physical index bit; bits >= nlocal are the rank bits
+        self.bit_of = [self.nqubits - 1 - q for q in range(self.nqubits)]
+        self.swap_chunk_bytes = swap_chunk_bytes
+        self.stats = {"exchanges": 0, "exchange_bytes": 0, "local_passes": 0, "skipped": 0,
+                      "relabelled_swaps": 0}
+        self.shard = backend.shard_zeros(self.nlocal, self.dtype, one_at_zero=(self.rank == 0))
+
+    # ------------------------------------------------------------------ helpers
+    def is_local(self, q):
+        return self.bit_of[q] < self.nlocal
+
+    def rank_bit(self, q):
+        """Value of global qubit q's index bit on this rank."""
+        return (self.rank >> (self.bit_of[q] - self.nlocal)) & 1
+
+    def _pseudo(self, bit):
+        """Backend entry points take qibo-style qubit numbers of an nlocal-qubit register."""
+        return self.nlocal - 1 - bit
+
+    def qubit_at(self, bit):
+        return self.bit_of.index(bit)
+
+    # ------------------------------------------------------------------ exchange
+    def swap_global_local(self, qglobal, qlocal):
+        """Exchange the roles of a global and a local qubit (ops.swap_pieces semantics)."""
+        gbit, lbit = self.bit_of[qglobal], self.bit_of[qlocal]
+        assert gbit >= self.nlocal > lbit
+        j = gbit - self.nlocal
+        peer = self.rank ^ (1 << j)
+        is_upper = (self.rank >> j) & 1
+        moved = self.backend.shard_exchange(self.shard, self.nlocal, lbit, peer, is_upper, self.comm,
+                                            self.swap_chunk_bytes)
+        self.bit_of[qglobal], self.bit_of[qlocal] = lbit, gbit
+        self.stats["exchanges"] += 1
+        self.stats["exchange_bytes"] += int(moved)
+
+    def _choose_victim(self, protected, lookahead):
+        """Local qubit whose next use as a non-diagonal target lies farthest in the future."""
+        best, best_dist = None, -1
+        for q in range(self.nqubits):
+            if not self.is_local(q) or q in protected:
+                continue
+            if self.dtype == "complex64" and self.bit_of[q] == 0:
+                continue  # 16-byte exchange granularity
+            dist = lookahead.get(q, 1 << 30)
+            if dist > best_dist:
+                best, best_dist = q, dist
+        if best is None:
+            raise RuntimeError("no local qubit available to swap with")
+        return best
+
+    def ensure_local(self, qubits, lookahead=None):
+        lookahead = lookahead or {}
+        for q in qubits:
+            if not self.is_local(q):
+                victim = self._choose_victim(set(qubits), lookahead)
+                self.swap_global_local(q, victim)
+
+    # ------------------------------------------------------------------ gate application
+    def apply_gate(self, gate, lookahead=None):
+        b = self.backend
+        name = gate.__class__.__name__
+        if getattr(gate, "name", "") == "fanout":
+            from . import gates as G
+
+            for t in gate.target_qubits:
+                self.apply_gate(G.CNOT(gate.control_qubits[0], t), lookahead)
+            return
+        targets = list(gate.target_qubits)
+        controls = list(gate.control_qubits)
+        op = GATE_OPS.get(name)
+
+        if op == "apply_swap" and not controls:
+            # relabel: the data does not move, the two logical qubits trade index bits
+            a, c = targets
+            self.bit_of[a], self.bit_of[c] = self.bit_of[c], self.bit_of[a]
+            self.stats["relabelled_swaps"] += 1
+            return
+
+        matrix = b._as_custom_matrix(gate)
+
+        if op in _SYMMETRIC_PHASE_OPS:
+            # phase on |1..1> of controls+target: symmetric in its qubits
+            qs = controls + targets
+            if any((not self.is_local(q)) and self.rank_bit(q) == 0 for q in qs):
+                self.stats["skipped"] += 1
+                return
+            local = [q for q in qs if self.is_local(q)]
+            phase = -1.0 if op == "apply_z" else complex(np.asarray(matrix).ravel()[0])
+            if not local:
+                b.shard_scale(self.shard, self.nlocal, phase)
+            else:
+                bits = sorted(self.bit_of[q] for q in local)
+                tbit = bits[0]
+                b._one_qubit_base(self.shard, self.nlocal, self._pseudo(tbit), op, matrix,
+                                  np.array(bits, dtype=np.int32) if len(bits) > 1 else None)
+            self.stats["local_passes"] += 1
+            return
+
+        # global controls: rank predicate
+        for q in controls:
+            if not self.is_local(q) and self.rank_bit(q) == 0:
+                self.stats["skipped"] += 1
+                return
+        lcontrols = [q for q in controls if self.is_local(q)]
+
+        gtargets = [q for q in targets if not self.is_local(q)]
+        if gtargets:
+            dense = self._dense_matrix(gate, matrix)
+            if is_diagonal_matrix(dense):
+                self._apply_restricted_diagonal(np.diagonal(dense), targets, lcontrols)
+                return
+            self.ensure_local(targets, lookahead)
+            # a victim may have been one of this gate's local controls: re-evaluate them
+            for q in controls:
+                if not self.is_local(q) and self.rank_bit(q) == 0:
+                    self.stats["skipped"] += 1
+                    return
+            lcontrols = [q for q in controls if self.is_local(q)]
+
+        self._apply_local(op, name, matrix, targets, lcontrols)
+
+    def _dense_matrix(self, gate, matrix):
+        from . import fusion
+
+        return fusion.target_only_matrix(gate, self.backend.custom_matrices)
+
+    def _apply_local(self, op, name, matrix, targets, lcontrols):
+        b = self.backend
+        n = self.nlocal
+        tb = [self.bit_of[q] for q in targets]
+        bits = sorted(tb + [self.bit_of[q] for q in lcontrols])
+        qubits = np.array(bits, dtype=np.int32) if lcontrols else None
+        pt = [self._pseudo(x) for x in tb]
+        if len(targets) == 1:
+            b._one_qubit_base(self.shard, n, pt[0], op or "apply_gate", matrix, qubits)
+        elif len(targets) == 2:
+            b._two_qubit_base(self.shard, n, pt[0], pt[1], op or "apply_two_qubit_gate", matrix, qubits)
+        else:
+            b._multi_qubit_base(self.shard, n, pt, matrix, np.array(bits, dtype=np.int32))
+        self.stats["local_passes"] += 1
+
+    def _apply_restricted_diagonal(self, diag, targets, lcontrols):
+        """Diagonal gate with some targets global: fix those bits to the rank's values."""
+        b = self.backend
+        t = len(targets)
+        d = np.asarray(diag).reshape((2,) * t)
+        index = tuple(self.rank_bit(q) if not self.is_local(q) else slice(None) for q in targets)
+        d = d[index]
+        ltargets = [q for q in targets if self.is_local(q)]
+        if ltargets:
+            d = np.asarray(d).reshape(-1)
+            self._apply_local(None, "Unitary", np.diag(d), ltargets, lcontrols)
+            return
+        phase = complex(d)
+        if not lcontrols:
+            b.shard_scale(self.shard, self.nlocal, phase)
+        else:
+            bits = sorted(self.bit_of[q] for q in lcontrols)
+            b._one_qubit_base(self.shard, self.nlocal, self._pseudo(bits[0]), "apply_z_pow",
+                              np.asarray(phase), np.array(bits, dtype=np.int32) if len(bits) > 1 else None)
+        self.stats["local_passes"] += 1
+
+    # ------------------------------------------------------------------ circuits
+    @staticmethod
+    def _needs_local(gate, custom_matrices):
+        """Qubits of `gate` that must be local for it to run (non-diagonal targets)."""
+        name = gate.__class__.__name__
+        op = GATE_OPS.get(name)
+        if op in _SYMMETRIC_PHASE_OPS or getattr(gate, "diagonal", False):
+            return []
+        if op == "apply_swap" and not gate.control_qubits:
+            return []
+        if name == "FusedGate":
+            from . import fusion
+
+            if is_diagonal_matrix(fusion.fused_matrix(gate, custom_matrices)):
+                return []
+        return list(gate.target_qubits)
+
+    def execute(self, queue):
+        """Apply a gate list; swap victims are chosen with a look-ahead over the list."""
+        needs = [self._needs_local(g, self.backend.custom_matrices) for g in queue]
+        # next_use[i][q] = distance from gate i to q's next appearance in `needs`
+        nxt = {}
+        table = [None] * len(queue)
+        for i in range(len(queue) - 1, -1, -1):
+            table[i] = dict(nxt)
+            for q in needs[i]:
+                nxt[q] = i
+        for i, gate in enumerate(queue):
+            look = {q: (j - i) for q, j in table[i].items()}
+            self.apply_gate(gate, look)
+        return self
+
+    # ------------------------------------------------------------------ results
+    def probabilities(self, qubits):
+        """Marginal distribution over logical `qubits` (replicated on every rank)."""
+        b = self.backend
+        qubits = list(qubits)
+        lq = [q for q in qubits if self.is_local(q)]
+        local = b.calculate_probabilities(self.shard, [self._pseudo(self.bit_of[q]) for q in lq],
+                                          self.nlocal)
+        out = b.engine.zeros((2,) * len(qubits), dtype=local.dtype, device=local.device) \
+            if qubits else b.engine.zeros((), dtype=local.dtype, device=local.device)
+        index = tuple(slice(None) if self.is_local(q) else self.rank_bit(q) for q in qubits)
+        out[index] = local.reshape((2,) * len(lq)) if lq else local.reshape(())
+        out = out.reshape(-1)
+        return self.comm.all_reduce_sum(out)
+
+    def norm2(self):
+        b = self.backend
+        val = b.calculate_norm(self.shard) ** 2
+        t = b.engine.tensor([val], dtype=b.engine.float64, device=self.shard.device)
+        return float(self.comm.all_reduce_sum(t)[0])
+
+    def to_numpy_full(self):
+        """Gather every shard and undo the qubit relabelling (small registers / tests only)."""
+        pieces = self.comm.all_gather(self.shard)
+        phys = np.concatenate([self.backend.to_numpy(p) for p in pieces])
+        n = self.nqubits
+        # axis a of the reshaped tensor is physical bit n-1-a; logical qubit q must end on axis q
+        t = phys.reshape((2,) * n)
+        axes = [n - 1 - self.bit_of[q] for q in range(n)]
+        return np.transpose(t, axes).reshape(-1)
+
+
+def execute_distributed_circuit(backend, circuit, initial_state=None, nshots=None, comm=None):
+    if initial_state is not None:
+        raise TypeError("distributed execution starts from |0...0>; initial states are not supported")
+    state = DistributedState(backend, circuit.nqubits, comm=comm)
+    state.execute(circuit.queue)
+    return state

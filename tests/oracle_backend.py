@@ -1,0 +1,78 @@
+"""TEST INFRASTRUCTURE: a numpy/oracle stand-in with the backend surface the distributed layer
+uses, so `qibojit_b200.distributed` can be exercised on CPU ranks (gloo, world_size 2+).
+Kernels = the CPU oracle; shard exchange = torch.distributed send/recv on CPU tensors."""
+
+import numpy as np
+import torch
+
+from oracle import oracle as O
+from qibojit_b200.matrices import CustomMatrices
+from tests import refdispatch as R
+
+
+class OracleBackend:
+    def __init__(self, dtype="complex128"):
+        self.dtype = dtype
+        self.custom_matrices = CustomMatrices(dtype)
+        self.engine = torch
+
+    # --- same helpers as B200Backend
+    def _as_custom_matrix(self, gate):
+        from qibojit_b200 import fusion
+
+        name = gate.__class__.__name__
+        if name == "FusedGate":
+            return fusion.fused_matrix(gate, self.custom_matrices)
+        if name == "FanOut":
+            return None
+        return gate.target_matrix(self.custom_matrices)
+
+    def to_numpy(self, x):
+        return x.numpy() if hasattr(x, "numpy") else np.asarray(x)
+
+    def _one_qubit_base(self, state, nqubits, target, kernel, gate, qubits):
+        R.one_qubit_base(O, state.numpy(), nqubits, target, kernel, gate, qubits)
+        return state
+
+    def _two_qubit_base(self, state, nqubits, t1, t2, kernel, gate, qubits):
+        R.two_qubit_base(O, state.numpy(), nqubits, t1, t2, kernel, gate, qubits)
+        return state
+
+    def _multi_qubit_base(self, state, nqubits, targets, gate, qubits):
+        R.multi_qubit_base(O, state.numpy(), nqubits, list(targets), gate, qubits)
+        return state
+
+    def zero_state(self, nqubits, dtype=None):
+        st = np.empty(1 << nqubits, dtype=dtype or self.dtype)
+        return torch.from_numpy(O.initial_state_vector(st))
+
+    def calculate_probabilities(self, state, qubits, nqubits):
+        return torch.from_numpy(O.calculate_probabilities(state.numpy(), list(qubits), nqubits))
+
+    def calculate_norm(self, state):
+        return float(np.linalg.norm(state.numpy()))
+
+    # --- shard primitives
+    def shard_zeros(self, nlocal, dtype, one_at_zero=False):
+        if one_at_zero:
+            return self.zero_state(nlocal, dtype)
+        return torch.zeros(1 << nlocal, dtype=getattr(torch, str(dtype)))
+
+    def shard_scale(self, shard, nlocal, phase):
+        shard.mul_(complex(phase))
+        return shard
+
+    def shard_exchange(self, shard, nlocal, lbit, peer, is_upper, comm, chunk_bytes=1 << 29):
+        dist = comm.dist
+        idx = np.arange(1 << nlocal)
+        sel = torch.from_numpy(idx[((idx >> lbit) & 1) == (0 if is_upper else 1)])
+        send = torch.view_as_real(shard[sel].contiguous())
+        recv = torch.empty_like(send)
+        if comm.rank < peer:
+            dist.send(send, peer, group=comm.group)
+            dist.recv(recv, peer, group=comm.group)
+        else:
+            dist.recv(recv, peer, group=comm.group)
+            dist.send(send, peer, group=comm.group)
+        shard[sel] = torch.view_as_complex(recv)
+        return send.numel() * send.element_size()

@@ -1,0 +1,123 @@
+"""world_size-2/4 gloo tests of the distributed state layer on CPU ranks (host-side logic:
+qubit map, rank predicates, diagonal restriction, swap scheduling, exchange pairing).  The
+local kernels are the CPU oracle through tests/oracle_backend.py."""
+
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _reference_state(circuit, dtype):
+    from oracle import oracle as O
+    from qibojit_b200 import fusion
+    from qibojit_b200.matrices import CustomMatrices
+    from tests import refdispatch as R
+
+    n = circuit.nqubits
+    mats = CustomMatrices("complex128")
+    st = np.zeros(1 << n, dtype=np.complex128)
+    st[0] = 1
+    for g in circuit.queue:
+        if g.name == "fanout":
+            for t in g.target_qubits:
+                st = R.einsum_apply(st, mats.X, [t], [g.control_qubits[0]], n)
+        else:
+            st = R.einsum_apply(st, fusion.target_only_matrix(g, mats), list(g.target_qubits),
+                                list(g.control_qubits), n)
+    return st.astype(dtype)
+
+
+def _test_circuits(n):
+    from qibojit_b200 import circuits, gates
+    from qibojit_b200.circuit import Circuit
+
+    rng = np.random.default_rng(3)
+    mixed = Circuit(n)
+    mixed.add(gates.H(q) for q in range(n))
+    mixed.add([gates.CNOT(0, n - 1), gates.CZ(1, 0), gates.CU1(0, 1, 0.3), gates.RZ(0, 0.7),
+               gates.Z(0), gates.U1(1, 0.2), gates.RZZ(0, 1, 0.4), gates.RZZ(0, n - 1, 0.9),
+               gates.CRZ(2, 0, 0.5), gates.CRZ(0, 1, 0.6), gates.TOFFOLI(0, 1, 2), gates.SWAP(0, n - 1),
+               gates.fSim(0, 2, 0.3, 0.8), gates.CCZ(0, 1, 2), gates.Y(0), gates.CY(1, 0),
+               gates.RX(1, 0.4), gates.SWAP(1, 2).controlled_by(0), gates.FanOut(0, 1, n - 1),
+               gates.Unitary(rng.standard_normal((4, 4)) + 1j * rng.standard_normal((4, 4)), 0, n - 2),
+               gates.Unitary(rng.standard_normal((8, 8)) + 0j, 1, n - 1, 0).controlled_by(2)])
+    return {"qft": circuits.qft(n), "variational": circuits.variational(n),
+            "variational_fused": circuits.variational(n).fuse(3), "supremacy": circuits.supremacy(n, depth=4),
+            "qv": circuits.quantum_volume(n, depth=3), "mixed": mixed, "mixed_fused": mixed.fuse(3)}
+
+
+def _worker(rank, world, port, n, dtype, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from qibojit_b200.distributed import Comm, DistributedState
+        from tests.oracle_backend import OracleBackend
+
+        results = {}
+        for name, circuit in _test_circuits(n).items():
+            b = OracleBackend(dtype)
+            ds = DistributedState(b, n, comm=Comm(), dtype=dtype)
+            ds.execute(circuit.queue)
+            full = ds.to_numpy_full()
+            probs = ds.probabilities([0, n - 1, 2]).numpy()
+            results[name] = (full, probs, dict(ds.stats), ds.norm2())
+        if rank == 0:
+            q.put(results)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n", [(2, 6), (4, 7)])
+@pytest.mark.parametrize("dtype", ["complex128", "complex64"])
+def test_distributed_state_matches_single_state(world, n, dtype):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000) + world
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, dtype, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    atol = 1e-5 if dtype == "complex64" else 1e-12
+    for name, circuit in _test_circuits(n).items():
+        full, probs, stats, norm2 = results[name]
+        ref = _reference_state(circuit, dtype)
+        np.testing.assert_allclose(full, ref, rtol=0, atol=atol, err_msg=name)
+        p = (np.abs(ref.astype(np.complex128)) ** 2).reshape((2,) * n)
+        unmeasured = tuple(a for a in range(n) if a not in (0, n - 1, 2))
+        p = np.transpose(p.sum(axis=unmeasured), [0, 2, 1]).ravel()  # axes (0, 2, n-1) -> (0, n-1, 2)
+        np.testing.assert_allclose(probs, p, rtol=0, atol=1e-5 if dtype == "complex64" else 1e-12, err_msg=name)
+        assert abs(norm2 - float(np.vdot(ref, ref).real)) < 1e-4
+    # the QFT's controlled phases and final swaps must not trigger exchanges beyond the H gates
+    assert results["qft"][2]["exchanges"] <= int(np.log2(world)) + 1
+    assert results["qft"][2]["relabelled_swaps"] == n // 2
+
+
+def test_lookahead_prefers_far_victims():
+    """Single-rank logic check of the swap victim choice (no process group needed)."""
+    from qibojit_b200.distributed import DistributedState
+
+    class FakeComm:
+        rank, world = 0, 1
+
+        def barrier(self):
+            pass
+
+    from tests.oracle_backend import OracleBackend
+
+    ds = DistributedState(OracleBackend(), 5, comm=FakeComm())
+    victim = ds._choose_victim({0}, {1: 3, 2: 50, 3: 7})
+    assert victim == 4  # never used again -> farthest
+    victim = ds._choose_victim({0, 4}, {1: 3, 2: 50, 3: 7})
+    assert victim == 2
