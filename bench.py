@@ -366,7 +366,7 @@ def run_ours(args):
         del out, probs
         torch.cuda.empty_cache()
     e2e_value = ngates / float(np.mean(e2e_times))
-    assert abs(host.sum() - 1.0) < 1e-6, host.sum()
+    assert abs(host.sum() - 1.0) < (1e-6 if dtype == 'complex128' else 1e-3), host.sum()
 
     cpu_gps, cpu_desc, cores = cpu_sample(args.workload, nqubits, dtype, args.cpu_seconds, fuse)
 

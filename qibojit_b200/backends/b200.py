@@ -590,16 +590,33 @@ class B200Backend(_QiboBackend):
 
     # ------------------------------------------------------------------ circuits
     def execute_circuit(self, circuit, initial_state=None, nshots=None):
-        """Minimal stand-in for qibo's ``Backend.execute_circuit``:
-        zero state (or a cast copy of `initial_state`), then every gate of ``circuit.queue``."""
+        """Stand-in for qibo's ``Backend.execute_circuit``: zero state (or a
+        cast copy of `initial_state`), then the circuit's queue.  The queue is compiled once per
+        (circuit, dtype) into multi-gate passes (``planner.Program``) so the whole circuit costs a
+        handful of passes over the state instead of one per gate; ``self.use_programs = False``
+        restores the gate-by-gate loop of the reference."""
         nqubits = circuit.nqubits
         if initial_state is None:
             state = self.zero_state(nqubits)
         else:
             state = self.cast(initial_state, copy=True)
+        if getattr(self, "use_programs", True) and nqubits >= 4 and len(circuit.queue) > 1:
+            return self.compile_circuit(circuit).run(state)
         for gate in circuit.queue:
             state = gate.apply(self, state, nqubits)
         return state
+
+    def compile_circuit(self, circuit, **options):
+        """Compile (and cache on the circuit object) the multi-gate pass program of `circuit`."""
+        from ..planner import Program
+
+        key = (self.dtype, self._device_index, len(circuit.queue), tuple(sorted(options.items())))
+        cache = circuit.__dict__.setdefault("_qj_programs", {})
+        prog = cache.get(key)
+        if prog is None:
+            prog = Program(self, circuit.queue, circuit.nqubits, dtype=self.dtype, **options)
+            cache[key] = prog
+        return prog
 
     def execute_distributed_circuit(self, circuit, initial_state=None, nshots=None):
         from ..distributed import execute_distributed_circuit

@@ -72,7 +72,7 @@ struct CMat {
 };
 
 template <typename T>
-struct Cx {
+struct __align__(2 * sizeof(T)) Cx {  // 16-byte (complex128) / 8-byte (complex64) vector accesses
     T re, im;
 };
 

@@ -1,0 +1,364 @@
+"""Pass planner: partitions a gate queue into multi-gate passes for ``qj_program_*``.
+
+Upstream, ``Backend.execute_circuit`` (qibo) and ``MultiGpuOps.apply_gates``
+(/root/reference/src/qibojit/backends/gpu.py:1467-1476) loop ``for gate in queue:
+apply_gate(...)``: one pass over the state per gate.  The per-gate kernels here already run at
+the HBM roofline, so the only way to make a circuit faster is fewer passes.  A *pass* keeps a
+set of T index bits "local" (resident in shared memory, always including the low contiguous run)
+and executes every gate whose non-diagonal targets are local; diagonal gates (Z, CZ, U1, CU1, RZ,
+...) and controls need no locality at all.  Consecutive diagonal gates are merged into phase
+tables over at most ``max_diag_bits`` index bits.
+
+The arithmetic of every gate is unchanged (same 2x2 / 4x4 complex mat-vec as
+gates.py:16-38, 118-193; diagonal factors are multiplied together on the host in double
+precision), only the order of memory traffic changes.
+"""
+
+import ctypes
+
+import numpy as np
+
+from . import _capi
+from . import fusion
+
+OP_DTYPE = np.dtype([
+    ("kind", "<i4"), ("ntargets", "<i4"), ("ncontrols", "<i4"), ("reserved", "<i4"),
+    ("data_offset", "<i8"),
+    ("targets", "<i4", (_capi.QJ_MAX_DIAG_BITS,)),
+    ("controls", "<i4", (_capi.QJ_MAX_QUBITS,)),
+])
+PASS_DTYPE = np.dtype([
+    ("nlocal", "<i4"), ("reserved", "<i4"), ("first_op", "<i8"), ("nops", "<i8"),
+    ("local_bits", "<i4", (_capi.QJ_MAX_LOCAL_BITS,)),
+])
+assert OP_DTYPE.itemsize == 264 and PASS_DTYPE.itemsize == 88
+
+# diagonal in the computational basis: no locality needed
+DIAGONAL_GATES = frozenset({
+    "I", "Z", "S", "SDG", "T", "TDG", "RZ", "U1", "CZ", "CRZ", "CU1", "CCZ", "RZZ",
+})
+
+DEFAULT_TILE_BITS = {"complex128": 12, "complex64": 13}
+DEFAULT_RUN_BITS = {"complex128": 5, "complex64": 6}
+MAX_TILE_BITS = {"complex128": 12, "complex64": 13}   # 64 KiB tiles, double-buffered per SM
+MAX_HI_BITS = 8
+MIN_QUBITS = 4
+
+
+class PlanOp:
+    """One operation in index-bit space.  kind: 'dense' (1 or 2 targets), 'diag', 'raw'."""
+
+    __slots__ = ("kind", "targets", "controls", "data", "gate", "bits")
+
+    def __init__(self, kind, targets=(), controls=(), data=None, gate=None):
+        self.kind = kind
+        self.targets = tuple(targets)    # dense: matrix-index bit j <-> targets[j]; diag: table bit j
+        self.controls = tuple(controls)
+        self.data = data
+        self.gate = gate
+        self.bits = frozenset(self.targets) | frozenset(self.controls)
+
+
+def _is_diagonal(gate):
+    name = gate.__class__.__name__
+    if name in DIAGONAL_GATES:
+        return True
+    return bool(getattr(gate, "diagonal", False)) and name != "FusedGate"
+
+
+def lower_gate(gate, nqubits, matrices):
+    """qibo-style gate -> list of PlanOps (index bit m = nqubits - 1 - q, cpu.py:610)."""
+    name = gate.__class__.__name__
+    if name == "FanOut" or getattr(gate, "name", None) == "fanout":  # cpu.py:417-431
+        c = nqubits - 1 - gate.control_qubits[0]
+        x = np.array([[0, 1], [1, 0]], dtype=np.complex128)
+        return [PlanOp("dense", (nqubits - 1 - t,), (c,), x) for t in gate.target_qubits]
+    if name == "M" or hasattr(gate, "coefficients"):
+        return [PlanOp("raw", gate=gate)]
+    targets = [nqubits - 1 - q for q in gate.target_qubits]
+    controls = [nqubits - 1 - q for q in gate.control_qubits]
+    nt = len(targets)
+    if nt > 2 and not _is_diagonal(gate):
+        return [PlanOp("raw", gate=gate)]
+    u = np.asarray(fusion.target_only_matrix(gate, matrices), dtype=np.complex128)
+    if nt <= _capi.QJ_MAX_DIAG_BITS and (_is_diagonal(gate) or _matrix_is_diagonal(u)):
+        # table bit j <-> targets reversed (first target = most significant matrix bit)
+        return [PlanOp("diag", tuple(targets[::-1]), tuple(controls), np.diagonal(u).copy())]
+    if nt > 2:
+        return [PlanOp("raw", gate=gate)]
+    return [PlanOp("dense", tuple(targets[::-1]), tuple(controls), u)]
+
+
+def _matrix_is_diagonal(u):
+    return u.ndim == 2 and not np.any(u - np.diag(np.diagonal(u)))
+
+
+# ------------------------------------------------------------------------------- passes
+def partition(ops, nqubits, tile_bits, run_bits):
+    """Greedy partition of PlanOps into segments: ('pass', local_bits, [ops]) or ('raw', op)."""
+    T = max(MIN_QUBITS, min(tile_bits, nqubits))
+    r = min(run_bits, T)
+    if T - r > MAX_HI_BITS:
+        r = T - MAX_HI_BITS
+    segments = []
+    remaining = list(ops)
+    allbits = frozenset(range(nqubits))
+    while remaining:
+        if remaining[0].kind == "raw":
+            segments.append(("raw", remaining.pop(0)))
+            continue
+        local = set(range(r))
+        blocked = set()
+        taken, rest = [], []
+        for i, op in enumerate(remaining):
+            if len(blocked) == nqubits:
+                rest.extend(remaining[i:])
+                break
+            if op.kind == "raw":
+                blocked = set(allbits)
+                rest.append(op)
+                continue
+            if blocked & op.bits:
+                blocked |= op.bits
+                rest.append(op)
+                continue
+            if op.kind == "diag":
+                taken.append(op)
+                continue
+            need = set(op.targets) - local
+            if len(local) + len(need) <= T:
+                local |= need
+                taken.append(op)
+            else:
+                blocked |= op.bits
+                rest.append(op)
+        b = 0
+        while len(local) < T:  # pad with the lowest free bits: longer contiguous runs
+            if b not in local:
+                local.add(b)
+            b += 1
+        segments.append(("pass", sorted(local), taken))
+        remaining = rest
+    return segments
+
+
+class _DiagAcc:
+    def __init__(self):
+        self.bits = []                      # table bit j <-> index bit bits[j]
+        self.table = np.ones(1, dtype=np.complex128)
+
+    def absorb(self, op):
+        # controls of a diagonal op are table bits whose 0-branch is the identity
+        obits = list(op.targets) + list(op.controls)
+        otab = np.ones(1 << len(obits), dtype=np.complex128)
+        nt = len(op.targets)
+        cmask = ((1 << len(op.controls)) - 1) << nt
+        idx = np.arange(1 << len(obits))
+        sel = (idx & cmask) == cmask
+        otab[sel] = np.asarray(op.data, dtype=np.complex128)[idx[sel] & ((1 << nt) - 1)]
+        for b in obits:
+            if b not in self.bits:
+                self.bits.append(b)
+                self.table = np.tile(self.table, 2)
+        i = np.arange(self.table.size)
+        gi = np.zeros_like(i)
+        for k, b in enumerate(obits):
+            gi |= ((i >> self.bits.index(b)) & 1) << k
+        self.table = self.table * otab[gi]
+
+    def finish(self, local_pos):
+        """-> PlanOp with control-like bits split off and table bits ordered by local position."""
+        bits, table = list(self.bits), self.table
+        controls = []
+        j = 0
+        while j < len(bits):
+            i = np.arange(table.size)
+            zero = table[((i >> j) & 1) == 0]
+            if np.all(zero == 1.0):
+                controls.append(bits.pop(j))
+                table = table[((i >> j) & 1) == 1]
+            else:
+                j += 1
+        if not bits and not controls and table[0] == 1.0:
+            return None
+        if bits:
+            order = sorted(range(len(bits)), key=lambda k: (local_pos.get(bits[k], 1 << 20) , bits[k]))
+            if order != list(range(len(bits))):
+                t = table.reshape((2,) * len(bits))          # axis a <-> table bit len-1-a
+                axes = [len(bits) - 1 - order[len(bits) - 1 - a] for a in range(len(bits))]
+                table = np.ascontiguousarray(np.transpose(t, axes)).reshape(-1)
+                bits = [bits[k] for k in order]
+        if np.all(table == 1.0) and not controls:
+            return None
+        return PlanOp("diag", tuple(bits), tuple(controls), table)
+
+
+def merge_diagonals(ops, local_bits, max_diag_bits):
+    """Merge commuting diagonal ops of one pass into phase tables (order-preserving w.r.t. every
+    dense op that targets one of their bits)."""
+    local_pos = {b: i for i, b in enumerate(local_bits)}
+    out, accs = [], []
+
+    def flush(acc):
+        accs.remove(acc)
+        op = acc.finish(local_pos)
+        if op is not None:
+            out.append(op)
+
+    for op in ops:
+        if op.kind == "diag":
+            obits = set(op.bits)
+            best, best_key = None, None
+            for acc in accs:  # an open table that shares a bit with the op and has room for it
+                abits = set(acc.bits)
+                if not (obits & abits) or len(obits | abits) > max_diag_bits:
+                    continue
+                key = (len(obits - abits), -len(obits & abits))
+                if best is None or key < best_key:
+                    best, best_key = acc, key
+            if best is None:
+                best = _DiagAcc()
+                accs.append(best)
+            best.absorb(op)
+            continue
+        for acc in [a for a in accs if set(a.bits) & set(op.targets)]:
+            flush(acc)
+        out.append(op)
+    for acc in list(accs):
+        flush(acc)
+    return out
+
+
+def plan_queue(queue, nqubits, matrices, tile_bits, run_bits, max_diag_bits=10):
+    """Gate queue -> [('pass', local_bits, [PlanOp]) | ('raw', gate)] (pure host logic)."""
+    ops = []
+    for gate in queue:
+        ops.extend(lower_gate(gate, nqubits, matrices))
+    out = []
+    for seg in partition(ops, nqubits, tile_bits, run_bits):
+        if seg[0] == "raw":
+            out.append(("raw", seg[1].gate))
+            continue
+        merged = merge_diagonals(seg[2], seg[1], min(max_diag_bits, _capi.QJ_MAX_DIAG_BITS))
+        if merged:
+            out.append(("pass", seg[1], merged))
+    return out
+
+
+# ------------------------------------------------------------------------------- programs
+class Program:
+    """A compiled gate queue: device-resident tile programs interleaved with raw gates that the
+    per-gate kernels execute (dense gates on >= 3 targets, measurements)."""
+
+    def __init__(self, backend, queue, nqubits, dtype=None, tile_bits=None, run_bits=None,
+                 max_diag_bits=10):
+        self.backend = backend
+        self.nqubits = int(nqubits)
+        self.dtype = str(dtype or backend.dtype)
+        self.tile_bits = min(int(tile_bits or DEFAULT_TILE_BITS[self.dtype]), MAX_TILE_BITS[self.dtype])
+        self.run_bits = int(run_bits or DEFAULT_RUN_BITS[self.dtype])
+        self.max_diag_bits = min(int(max_diag_bits), _capi.QJ_MAX_DIAG_BITS)
+        if self.nqubits < MIN_QUBITS:
+            raise ValueError(f"tile programs need at least {MIN_QUBITS} qubits")
+        self.ngates = len(queue)
+        self.segments = []       # ('program', handle, npasses) | ('raw', gate)
+        self.passes = []         # [(local_bits, [PlanOp])] for inspection
+        pending = []
+        for seg in plan_queue(queue, self.nqubits, backend.custom_matrices, self.tile_bits,
+                              self.run_bits, self.max_diag_bits):
+            if seg[0] == "raw":
+                self._flush(pending)
+                pending = []
+                self.segments.append(("raw", seg[1]))
+            else:
+                pending.append((seg[1], seg[2]))
+        self._flush(pending)
+
+    # -- serialisation
+    def _flush(self, passes):
+        if not passes:
+            return
+        np_dtype = np.dtype(self.dtype)
+        nops = sum(len(p[1]) for p in passes)
+        op_arr = np.zeros(nops, dtype=OP_DTYPE)
+        pass_arr = np.zeros(len(passes), dtype=PASS_DTYPE)
+        chunks, offset, k = [], 0, 0
+        for pi, (local_bits, ops) in enumerate(passes):
+            pass_arr[pi]["nlocal"] = len(local_bits)
+            pass_arr[pi]["first_op"] = k
+            pass_arr[pi]["nops"] = len(ops)
+            pass_arr[pi]["local_bits"][:len(local_bits)] = local_bits
+            for op in ops:
+                rec = op_arr[k]
+                data = np.ascontiguousarray(np.asarray(op.data, dtype=np_dtype).reshape(-1))
+                if op.kind == "dense":
+                    rec["kind"] = _capi.QJ_OPK_DENSE1 if len(op.targets) == 1 else _capi.QJ_OPK_DENSE2
+                else:
+                    rec["kind"] = _capi.QJ_OPK_DIAG
+                rec["ntargets"] = len(op.targets)
+                rec["targets"][:len(op.targets)] = op.targets
+                rec["ncontrols"] = len(op.controls)
+                rec["controls"][:len(op.controls)] = op.controls
+                rec["data_offset"] = offset
+                chunks.append(data)
+                offset += data.size
+                k += 1
+        data = np.concatenate(chunks) if chunks else np.zeros(0, dtype=np_dtype)
+        b = self.backend
+        handle = ctypes.c_void_p()
+        _capi.check(b._lib.qj_program_create(
+            b._handle(), _capi.QJ_C128 if self.dtype == "complex128" else _capi.QJ_C64, self.nqubits,
+            pass_arr.ctypes.data, len(passes), op_arr.ctypes.data, nops, data.ctypes.data,
+            int(data.size), ctypes.byref(handle)))
+        self.segments.append(("program", handle, len(passes)))
+        self.passes.extend(passes)
+
+    # -- execution
+    def run(self, state):
+        b = self.backend
+        if state.numel() != (1 << self.nqubits) or str(state.dtype).replace("torch.", "") != self.dtype:
+            raise ValueError("state does not match the program's qubit count / dtype")
+        for seg in self.segments:
+            if seg[0] == "program":
+                _capi.check(b._lib.qj_program_run(b._handle(), seg[1], state.data_ptr()))
+            else:
+                state = seg[1].apply(b, state, self.nqubits)
+        return state
+
+    def stats(self):
+        """{'launches', 'rounds', 'micro_ops', 'raw_gates'} summed over the segments."""
+        out = dict(launches=0, rounds=0, micro_ops=0, raw_gates=0, passes=len(self.passes))
+        for seg in self.segments:
+            if seg[0] == "raw":
+                out["raw_gates"] += 1
+                continue
+            a, r, m = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+            _capi.check(self.backend._lib.qj_program_stats(seg[1], ctypes.byref(a), ctypes.byref(r),
+                                                          ctypes.byref(m)))
+            out["launches"] += a.value
+            out["rounds"] += r.value
+            out["micro_ops"] += m.value
+        return out
+
+    def launches(self):
+        """[(segment handle, launch index)] of every kernel launch, for per-pass timing."""
+        out = []
+        for seg in self.segments:
+            if seg[0] != "program":
+                continue
+            a = ctypes.c_int64()
+            _capi.check(self.backend._lib.qj_program_stats(seg[1], ctypes.byref(a), None, None))
+            out.extend((seg[1], i) for i in range(a.value))
+        return out
+
+    def close(self):
+        for seg in self.segments:
+            if seg[0] == "program" and seg[1]:
+                self.backend._lib.qj_program_destroy(self.backend._handle(), seg[1])
+        self.segments = []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -89,3 +89,28 @@ def einsum_apply(state, matrix, targets, controls, nqubits):
     out = np.moveaxis(out, list(range(k)), axes)
     psi[tuple(sl)] = out
     return psi.reshape(-1)
+
+
+def random_unitary(dim, seed):
+    rng = np.random.default_rng(seed + 104729)
+    z = rng.standard_normal((dim, dim)) + 1j * rng.standard_normal((dim, dim))
+    q, r = np.linalg.qr(z)
+    d = np.diagonal(r)
+    return q * (d / np.abs(d))
+
+
+def reference_run(state, gate_list, nqubits):
+    """Gate-by-gate einsum application of gate objects (complex128)."""
+    from qibojit_b200 import fusion
+    from qibojit_b200.matrices import CustomMatrices
+
+    mats = CustomMatrices("complex128")
+    ref = np.array(state, dtype=np.complex128)
+    for g in gate_list:
+        if g.name == "fanout":
+            for tq in g.target_qubits:
+                ref = einsum_apply(ref, mats.X, [tq], [g.control_qubits[0]], nqubits)
+        else:
+            ref = einsum_apply(ref, fusion.target_only_matrix(g, mats), list(g.target_qubits),
+                               list(g.control_qubits), nqubits)
+    return ref
