@@ -156,20 +156,25 @@ int qj_swap_unpack(qj_handle *h, void *local, const void *buf, int dtype, int nl
  * gate is one pass over the state.  A pass stages tiles of 2^nlocal amplitudes (the index bits
  * `local_bits`, which must start with the contiguous run 0,1,..,r-1) in shared memory and applies
  * all of its ops to the tile before writing it back: ONE HBM pass for the whole op list.
+ * Inside a pass the ops are grouped into ROUNDS: in a round every thread holds the 2^nreg
+ * amplitudes spanned by the round's register bits (local bits; complex128: nreg = 4,
+ * complex64: nreg = 5 and index bit 0 must be one of them) and applies the round's ops to them.
  *   QJ_OPK_DENSE1 / QJ_OPK_DENSE2: the arithmetic of {,multicontrol_}apply_gate_kernel and
  *     {,multicontrol_}apply_two_qubit_gate_kernel (gates.py:16-38, 118-193); targets must be
- *     local bits of the pass, targets[j] is the index bit addressed by matrix-index bit j
+ *     register bits of the round, targets[j] is the index bit addressed by matrix-index bit j
  *     (the reversed-target convention of cpu.py:594-596); controls may be any index bits.
  *   QJ_OPK_DIAG: multiply amplitude i by table[sum_j bit(i, targets[j]) << j] when every control
  *     bit of i is 1 -- a product of diagonal gates (apply_z / apply_z_pow, gates.py:82-114, and
  *     any other diagonal matrix) merged on the host; its bits may be any index bits.
  * `data` (HOST, complex in the state dtype) holds the row-major matrices and the tables; every op
- * owns its own range starting at data_offset.  Ops of a pass are applied in order.            */
+ * owns its own range starting at data_offset.  Rounds of a pass and ops of a round are applied
+ * in order.                                                                                    */
 #define QJ_OPK_DENSE1 1
 #define QJ_OPK_DENSE2 2
 #define QJ_OPK_DIAG 3
 #define QJ_MAX_DIAG_BITS 12
 #define QJ_MAX_LOCAL_BITS 16
+#define QJ_MAX_REG_BITS 8
 
 typedef struct qj_op_desc {
     int32_t kind;
@@ -181,19 +186,27 @@ typedef struct qj_op_desc {
     int32_t controls[QJ_MAX_QUBITS];
 } qj_op_desc;
 
-typedef struct qj_pass_desc {
-    int32_t nlocal;                   /* 3 .. 14 */
+typedef struct qj_round_desc {
+    int32_t nreg;                     /* 4 (complex128) / 5 (complex64) */
     int32_t reserved;
-    int64_t first_op;                 /* range of this pass in the `ops` array */
+    int64_t first_op;                 /* range of this round in the `ops` array */
     int64_t nops;
+    int32_t reg_bits[QJ_MAX_REG_BITS]; /* strictly ascending index bits, a subset of local_bits */
+} qj_round_desc;
+
+typedef struct qj_pass_desc {
+    int32_t nlocal;                   /* 6 .. 12 (complex128) / 13 (complex64) */
+    int32_t reserved;
+    int64_t first_round;              /* range of this pass in the `rounds` array */
+    int64_t nrounds;
     int32_t local_bits[QJ_MAX_LOCAL_BITS]; /* strictly ascending index bits */
 } qj_pass_desc;
 
 typedef struct qj_program qj_program;
 
 int qj_program_create(qj_handle *h, int dtype, int nqubits, const qj_pass_desc *passes, int npasses,
-                      const qj_op_desc *ops, int64_t nops, const void *data, int64_t ndata,
-                      qj_program **out);
+                      const qj_round_desc *rounds, int64_t nrounds, const qj_op_desc *ops,
+                      int64_t nops, const void *data, int64_t ndata, qj_program **out);
 /* apply every pass of the program to `state` (DEVICE pointer, 2^nqubits amplitudes) */
 int qj_program_run(qj_handle *h, const qj_program *p, void *state);
 /* one kernel launch of the program (bench/profiling: per-pass timing) */

@@ -46,7 +46,7 @@ SIGNATURES = {
     "qj_swap_pieces_peer": (_I, [_P, _P, _P, _I, _I, _I, _I]),
     "qj_swap_pack": (_I, [_P, _P, _P, _I, _I, _I, _I, _L, _L]),
     "qj_swap_unpack": (_I, [_P, _P, _P, _I, _I, _I, _I, _L, _L]),
-    "qj_program_create": (_I, [_P, _I, _I, _P, _I, _P, _L, _P, _L, _c.POINTER(_P)]),
+    "qj_program_create": (_I, [_P, _I, _I, _P, _I, _P, _L, _P, _L, _P, _L, _c.POINTER(_P)]),
     "qj_program_run": (_I, [_P, _P, _P]),
     "qj_program_run_launch": (_I, [_P, _P, _P, _I]),
     "qj_program_stats": (_I, [_P, _c.POINTER(_L), _c.POINTER(_L), _c.POINTER(_L)]),
@@ -54,7 +54,7 @@ SIGNATURES = {
 }
 
 QJ_OPK_DENSE1, QJ_OPK_DENSE2, QJ_OPK_DIAG = 1, 2, 3
-QJ_MAX_DIAG_BITS, QJ_MAX_LOCAL_BITS, QJ_MAX_QUBITS = 12, 16, 48
+QJ_MAX_DIAG_BITS, QJ_MAX_LOCAL_BITS, QJ_MAX_QUBITS, QJ_MAX_REG_BITS = 12, 16, 48, 8
 
 _lib = None
 

@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libqibojit_b200.so")
-SOURCES = ["capi.cu", "gate_kernels.cu", "tile_kernels.cu", "ops_kernels.cu", "block_kernels.cu"]
+SOURCES = ["capi.cu", "gate_kernels.cu", "tile_kernels.cu", "ops_kernels.cu", "pass_kernels.cu"]
 HEADERS = ["common.cuh", os.path.join("..", "..", "include", "qibojit_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

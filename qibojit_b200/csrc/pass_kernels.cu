@@ -1,0 +1,1071 @@
+// pass_kernels.cu -- multi-gate passes ("tile programs") for sm_100a.
+//
+// The per-gate kernels (gate_kernels.cu) already run at the HBM roofline, so the time of a
+// circuit is the number of passes over the state.  This kernel removes passes: a CTA stages a
+// tile of 2^T amplitudes in shared memory -- the low r index bits (a contiguous run, so global
+// traffic is made of whole 2^r-amplitude segments) plus T-r arbitrary higher index bits -- and
+// applies a whole PROGRAM of gates to it before writing it back.
+//
+// Execution model (the schedule itself is made on the host, qibojit_b200/planner.py):
+//   * the program of a pass is a list of ROUNDS.  In a round every thread owns 16 16-byte
+//     vectors of the tile = the 2^J amplitudes spanned by J "register" bits (complex128: J = 4;
+//     complex64: J = 5, index bit 0 -- the second amplitude of a vector -- always being one of
+//     them).  It gathers them from shared memory, applies every op of the round in registers,
+//     and scatters them back: shared memory is read and written once per round, not per gate.
+//   * ops: dense 2x2 / 4x4 on register slots (controls may be register slots -> element mask,
+//     other tile bits -> thread predicate, bits outside the tile -> tile predicate), X / SWAP as
+//     register renaming, and diagonal phase tables.  A table is sliced on the host along its
+//     register bits, so a slice is ONE look-up per thread (index = fields of the thread's tile
+//     position | a tile-constant part) followed by a complex multiply of the selected elements;
+//     +-1 tables become sign flips.
+//   * the whole program (rounds, op headers, gate matrices) is copied to shared memory once
+//     per CTA and read with warp-uniform (broadcast) loads; only phase tables stay in global
+//     memory (L1-resident).
+//   * shared-memory layout: 16-byte vectors, XOR swizzle of the low three vector-index bits with
+//     the three-bit groups above them; the host orders the thread bits of every round so that
+//     the eight lanes of a quarter warp hit eight different bank groups whatever the register
+//     bits are.
+//   * 256 threads and one 64 KiB tile per CTA, two CTAs per SM: while one CTA waits for its
+//     tile (LDGSTS) or drains its stores the other one computes.
+//
+// Arithmetic contract per op: gates.py:16-38 (one target), gates.py:118-193 (two targets),
+// gates.py:82-114 (diagonals, pre-multiplied into tables on the host).
+
+#include <algorithm>
+#include <complex>
+#include <vector>
+
+#include "common.cuh"
+
+namespace qj {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kVecRegBits = 4;          // a thread holds 2^4 vectors per round
+constexpr int kMaxTileVecBits = 12;     // 64 KiB tiles
+constexpr int kMinTileBits = 6;
+constexpr int kMaxHiBits = 8;
+constexpr int kMaxBlobUnits = (40 << 10) / 16;   // program image in shared memory
+constexpr int kMaxOuter = 512;
+
+template <typename T>
+struct Lay;
+template <>
+struct Lay<double> {
+    static constexpr int J = 4, N = 16, VS = 0;
+};
+template <>
+struct Lay<float> {
+    static constexpr int J = 5, N = 32, VS = 1;
+};
+
+// dispatch codes
+enum {
+    C_DENSE1C = 0,    // + slot
+    C_DENSE1R = 8,    // + slot (real matrix)
+    C_PERM1 = 16,     // + slot (X)
+    C_DENSE2 = 24,    // + pair index (a < b): b (b - 1) / 2 + a
+    C_PERM2 = 40,     // + pair index (SWAP)
+    C_DIAG1 = 56,     // one table look-up per thread, complex multiply of the masked elements
+    C_SIGN1 = 57,     // ... table of +-1: sign flip
+    C_DIAGC = 58,     // constant phase (payload)
+    C_SIGNC = 59,     // constant -1
+    C_DIAGN = 60,     // general: one look-up per element
+};
+
+struct PassGeom {
+    int T, r, nh;          // tile bits, run bits (amplitudes), high local bits
+    int hibit[kMaxHiBits];
+    int npos;
+    int pos[QJ_MAX_QUBITS];
+    int64_t ntiles;
+    int blob_units;        // program image, 16-byte units
+};
+
+// ---- program image (16-byte units) -------------------------------------------------------------
+// unit 0            : {nrounds, nouter, off_rounds, off_outer}
+// rounds, 3 units   : {first_unit, nops, vd0 | vd1 << 16, vd2 | vd3 << 16}
+//                     {td[0..7] as uint16}  {tpos[0..7] as uint8, 0, 0}
+// outers, 2 units   : {ocmask lo, ocmask hi, nbits, src[0..3]} {src[4..11], dst packed 4 bit x 12 ...}
+// ops               : 2-unit header + payload
+struct HostOuter {
+    uint64_t ocmask = 0;
+    int nbits = 0;
+    uint8_t src[12] = {0}, dst[12] = {0};
+};
+
+__host__ __device__ __forceinline__ uint32_t swz_vec(uint32_t v) {
+    return v ^ (((v >> 3) ^ (v >> 6) ^ (v >> 9)) & 7u);
+}
+
+template <typename T>
+__device__ __forceinline__ void cmul_acc(T &ar, T &ai, T gr, T gi, T xr, T xi) {
+    ar = fma(gr, xr, ar);
+    ar = fma(-gi, xi, ar);
+    ai = fma(gr, xi, ai);
+    ai = fma(gi, xr, ai);
+}
+
+__device__ __forceinline__ constexpr int insert0(int p, int a) { return ((p >> a) << (a + 1)) | (p & ((1 << a) - 1)); }
+
+// payload readers: NW 32-bit words from 16-byte aligned shared memory (warp-uniform address)
+template <int NU>
+__device__ __forceinline__ void load_units(const uint4 *p, double (&d)[2 * NU]) {
+#pragma unroll
+    for (int i = 0; i < NU; i++) {
+        const uint4 q = p[i];
+        d[2 * i] = __hiloint2double(int(q.y), int(q.x));
+        d[2 * i + 1] = __hiloint2double(int(q.w), int(q.z));
+    }
+}
+template <int NU>
+__device__ __forceinline__ void load_units(const uint4 *p, float (&d)[4 * NU]) {
+#pragma unroll
+    for (int i = 0; i < NU; i++) {
+        const uint4 q = p[i];
+        d[4 * i] = __uint_as_float(q.x); d[4 * i + 1] = __uint_as_float(q.y);
+        d[4 * i + 2] = __uint_as_float(q.z); d[4 * i + 3] = __uint_as_float(q.w);
+    }
+}
+
+// ---- ops on the register amplitudes ---------------------------------------------------------------
+template <typename T, int A, bool REAL>
+__device__ __forceinline__ void op_dense1(Cx<T> (&x)[Lay<T>::N], const uint4 *pay, uint32_t emask) {
+    constexpr int N = Lay<T>::N;
+    if constexpr (A < Lay<T>::J) {
+        constexpr int NS = REAL ? 4 : 8;                 // scalars in the payload (a whole number of units)
+        T m[NS];
+        load_units<NS * sizeof(T) / 16>(pay, m);
+#pragma unroll
+        for (int p = 0; p < N / 2; p++) {
+            const int e0 = insert0(p, A), e1 = e0 | (1 << A);
+            if (!((emask >> e0) & 1u)) continue;
+            const Cx<T> s0 = x[e0], s1 = x[e1];
+            Cx<T> y0, y1;
+            if (REAL) {
+                y0.re = fma(m[0], s0.re, m[1] * s1.re);
+                y0.im = fma(m[0], s0.im, m[1] * s1.im);
+                y1.re = fma(m[2], s0.re, m[3] * s1.re);
+                y1.im = fma(m[2], s0.im, m[3] * s1.im);
+            } else {
+                y0.re = m[0] * s0.re; y0.im = m[0] * s0.im;
+                y0.re = fma(-m[1], s0.im, y0.re); y0.im = fma(m[1], s0.re, y0.im);
+                cmul_acc(y0.re, y0.im, m[2], m[3], s1.re, s1.im);
+                y1.re = m[4] * s0.re; y1.im = m[4] * s0.im;
+                y1.re = fma(-m[5], s0.im, y1.re); y1.im = fma(m[5], s0.re, y1.im);
+                cmul_acc(y1.re, y1.im, m[6], m[7], s1.re, s1.im);
+            }
+            x[e0] = y0; x[e1] = y1;
+        }
+    }
+}
+
+// two-target gate: matrix-index bit 0 <-> slot A, bit 1 <-> slot B (A < B)
+template <typename T, int A, int B>
+__device__ __forceinline__ void op_dense2(Cx<T> (&x)[Lay<T>::N], const uint4 *pay, uint32_t emask) {
+    constexpr int N = Lay<T>::N;
+    if constexpr (B < Lay<T>::J) {
+        constexpr int RU = 8 * sizeof(T) / 16;           // units per matrix row (4 complex)
+#pragma unroll
+        for (int p = 0; p < N / 4; p++) {
+            const int e0 = insert0(insert0(p, A), B);
+            if (!((emask >> e0) & 1u)) continue;
+            Cx<T> s[4], y[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) s[j] = x[e0 | ((j & 1) << A) | ((j >> 1) << B)];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                T g[8];
+                load_units<RU>(pay + i * RU, g);
+                T ar = g[0] * s[0].re, ai = g[0] * s[0].im;
+                ar = fma(-g[1], s[0].im, ar); ai = fma(g[1], s[0].re, ai);
+#pragma unroll
+                for (int j = 1; j < 4; j++) cmul_acc(ar, ai, g[2 * j], g[2 * j + 1], s[j].re, s[j].im);
+                y[i].re = ar; y[i].im = ai;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; i++) x[e0 | ((i & 1) << A) | ((i >> 1) << B)] = y[i];
+        }
+    }
+}
+
+template <typename T, int A>
+__device__ __forceinline__ void op_perm1(Cx<T> (&x)[Lay<T>::N], uint32_t emask) {
+    constexpr int N = Lay<T>::N;
+    if constexpr (A < Lay<T>::J) {
+#pragma unroll
+        for (int p = 0; p < N / 2; p++) {
+            const int e0 = insert0(p, A), e1 = e0 | (1 << A);
+            if (!((emask >> e0) & 1u)) continue;
+            const Cx<T> t = x[e0]; x[e0] = x[e1]; x[e1] = t;
+        }
+    }
+}
+
+template <typename T, int A, int B>
+__device__ __forceinline__ void op_perm2(Cx<T> (&x)[Lay<T>::N], uint32_t emask) {
+    constexpr int N = Lay<T>::N;
+    if constexpr (B < Lay<T>::J) {
+#pragma unroll
+        for (int p = 0; p < N / 4; p++) {
+            const int e0 = insert0(insert0(p, A), B);
+            if (!((emask >> e0) & 1u)) continue;
+            const int ea = e0 | (1 << A), eb = e0 | (1 << B);
+            const Cx<T> t = x[ea]; x[ea] = x[eb]; x[eb] = t;
+        }
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ void mul_masked(Cx<T> (&x)[Lay<T>::N], uint32_t emask, T pr, T pi) {
+#pragma unroll
+    for (int e = 0; e < Lay<T>::N; e++) {
+        if (!((emask >> e) & 1u)) continue;
+        const Cx<T> v = x[e];
+        x[e].re = fma(pr, v.re, -pi * v.im);
+        x[e].im = fma(pr, v.im, pi * v.re);
+    }
+}
+
+__device__ __forceinline__ double flip(double v, uint32_t s) {
+    return __hiloint2double(int(uint32_t(__double2hiint(v)) ^ s), __double2loint(v));
+}
+__device__ __forceinline__ float flip(float v, uint32_t s) { return __uint_as_float(__float_as_uint(v) ^ s); }
+
+template <typename T>
+__device__ __forceinline__ void flip_masked(Cx<T> (&x)[Lay<T>::N], uint32_t emask, uint32_t s) {
+#pragma unroll
+    for (int e = 0; e < Lay<T>::N; e++) {
+        if (!((emask >> e) & 1u)) continue;
+        x[e].re = flip(x[e].re, s);
+        x[e].im = flip(x[e].im, s);
+    }
+}
+
+__device__ __forceinline__ uint32_t sign_of(double v) { return uint32_t(__double2hiint(v)) & 0x80000000u; }
+__device__ __forceinline__ uint32_t sign_of(float v) { return __float_as_uint(v) & 0x80000000u; }
+
+__device__ __forceinline__ Cx<double> ldg_cx(const Cx<double> *p) {
+    const double2 v = __ldg(reinterpret_cast<const double2 *>(p));
+    Cx<double> c; c.re = v.x; c.im = v.y;
+    return c;
+}
+__device__ __forceinline__ Cx<float> ldg_cx(const Cx<float> *p) {
+    const float2 v = __ldg(reinterpret_cast<const float2 *>(p));
+    Cx<float> c; c.re = v.x; c.im = v.y;
+    return c;
+}
+
+__device__ __forceinline__ int field_of(uint32_t base, uint32_t fl) {
+    return int(((base >> (fl & 255u)) & ((1u << ((fl >> 8) & 255u)) - 1u)) << (fl >> 16));
+}
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(
+                     static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst))),
+                 "l"(gmem_src)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+#define QJ_SLOT_CASES(CODE, CALL)                  \
+    case CODE + 0: { CALL(0); } break;             \
+    case CODE + 1: { CALL(1); } break;             \
+    case CODE + 2: { CALL(2); } break;             \
+    case CODE + 3: { CALL(3); } break;             \
+    case CODE + 4: { CALL(4); } break;
+#define QJ_PAIR_CASES(CODE, CALL)                  \
+    case CODE + 0: { CALL(0, 1); } break;          \
+    case CODE + 1: { CALL(0, 2); } break;          \
+    case CODE + 2: { CALL(1, 2); } break;          \
+    case CODE + 3: { CALL(0, 3); } break;          \
+    case CODE + 4: { CALL(1, 3); } break;          \
+    case CODE + 5: { CALL(2, 3); } break;          \
+    case CODE + 6: { CALL(0, 4); } break;          \
+    case CODE + 7: { CALL(1, 4); } break;          \
+    case CODE + 8: { CALL(2, 4); } break;          \
+    case CODE + 9: { CALL(3, 4); } break;
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 2)
+k_pass(Cx<T> *__restrict__ state, const __grid_constant__ PassGeom pg, const uint4 *__restrict__ blob,
+       const Cx<T> *__restrict__ tables) {
+    constexpr int N = Lay<T>::N;
+    constexpr int VS = Lay<T>::VS;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+
+    const int tid = threadIdx.x;
+    const int Tv = pg.T - VS;                     // tile bits in vectors
+    const int nvec = 1 << Tv;
+    const int rv = pg.r - VS;                     // run bits in vectors
+    const int rvmask = (1 << rv) - 1;
+    uint4 *const tilev = reinterpret_cast<uint4 *>(smem_raw);
+    uint4 *const prog = tilev + nvec;
+    int64_t *const s_runoff = reinterpret_cast<int64_t *>(prog + pg.blob_units);   // in vectors
+    int32_t *const s_outer = reinterpret_cast<int32_t *>(s_runoff + (1 << pg.nh));
+    uint4 *const gvec = reinterpret_cast<uint4 *>(state);
+
+    for (int i = tid; i < pg.blob_units; i += kThreads) prog[i] = __ldg(blob + i);
+    for (int run = tid; run < (1 << pg.nh); run += kThreads) {
+        int64_t off = 0;
+        for (int b = 0; b < pg.nh; b++) off |= int64_t((run >> b) & 1) << (pg.hibit[b] - VS);
+        s_runoff[run] = off;
+    }
+    __syncthreads();
+    const uint4 hdr = prog[0];
+    const int nrounds = int(hdr.x), nouter = int(hdr.y);
+    const uint4 *const rounds = prog + hdr.z;
+    const uint4 *const outers = prog + hdr.w;
+
+    const bool live = tid < (1 << (Tv - kVecRegBits));
+
+    for (int64_t tile_id = blockIdx.x; tile_id < pg.ntiles; tile_id += gridDim.x) {
+        // tile base: insert zeros at the high local bits
+        int64_t tb = tile_id;
+#pragma unroll 1
+        for (int j = 0; j < pg.npos; j++) {
+            const int p = pg.pos[j];
+            tb = ((tb >> p) << (p + 1)) | (tb & ((int64_t(1) << p) - 1));
+        }
+        const int64_t base_amp = tb << pg.r;
+        const int64_t base_vec = base_amp >> VS;
+
+        // ---- load (asynchronous copies straight into the swizzled tile)
+        for (int lv = tid; lv < nvec; lv += kThreads)
+            cp_async16(tilev + swz_vec(uint32_t(lv)), gvec + base_vec + s_runoff[lv >> rv] + (lv & rvmask));
+        // per-op tile constants: outer control predicate and outer part of the table index
+        for (int m = tid; m < nouter; m += kThreads) {
+            const uint4 o0 = outers[2 * m], o1 = outers[2 * m + 1];
+            const uint64_t ocmask = uint64_t(o0.x) | (uint64_t(o0.y) << 32);
+            int32_t v = 0;
+            if ((uint64_t(base_amp) & ocmask) != ocmask) {
+                v = -1;
+            } else {
+                const int nb = int(o0.z);
+                const uint32_t srcw[3] = {o0.w, o1.x, o1.y};
+                const uint32_t dstw[2] = {o1.z, o1.w};
+                for (int b = 0; b < nb; b++) {
+                    const int src = (srcw[b >> 2] >> ((b & 3) * 8)) & 255;
+                    const int dst = (dstw[b >> 3] >> ((b & 7) * 4)) & 15;
+                    v |= int32_t((base_amp >> src) & 1) << dst;
+                }
+            }
+            s_outer[m] = v;
+        }
+        cp_async_wait_all();
+        __syncthreads();
+
+        // ---- rounds
+#pragma unroll 1
+        for (int rd = 0; rd < nrounds; rd++) {
+            const uint4 r0 = rounds[3 * rd], r1 = rounds[3 * rd + 1], r2 = rounds[3 * rd + 2];
+            if (live) {
+                uint32_t vd[4] = {r0.z & 0xffffu, r0.z >> 16, r0.w & 0xffffu, r0.w >> 16};
+                const uint32_t tdw[4] = {r1.x, r1.y, r1.z, r1.w};
+                uint32_t S = 0, base = 0;
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    if ((tid >> k) & 1) {
+                        S ^= (tdw[k >> 1] >> ((k & 1) * 16)) & 0xffffu;
+                        base |= 1u << (((k < 4 ? r2.x : r2.y) >> ((k & 3) * 8)) & 255u);
+                    }
+                }
+                Cx<T> x[N];
+#pragma unroll
+                for (int v = 0; v < 16; v++) {
+                    const uint32_t off = S ^ ((v & 1) ? vd[0] : 0u) ^ ((v & 2) ? vd[1] : 0u) ^
+                                         ((v & 4) ? vd[2] : 0u) ^ ((v & 8) ? vd[3] : 0u);
+                    const uint4 q = *reinterpret_cast<const uint4 *>(smem_raw + off);
+                    if constexpr (sizeof(T) == 8) {
+                        x[v].re = __hiloint2double(int(q.y), int(q.x));
+                        x[v].im = __hiloint2double(int(q.w), int(q.z));
+                    } else {
+                        x[2 * v].re = __uint_as_float(q.x); x[2 * v].im = __uint_as_float(q.y);
+                        x[2 * v + 1].re = __uint_as_float(q.z); x[2 * v + 1].im = __uint_as_float(q.w);
+                    }
+                }
+
+                const uint4 *op = prog + r0.x;
+                const int nops = int(r0.y);
+#pragma unroll 1
+                for (int i = 0; i < nops; i++) {
+                    const uint4 h0 = op[0], h1 = op[1];
+                    const uint4 *pay = op + 2;
+                    op += h0.x >> 16;
+                    const uint32_t code = h0.x & 0xffffu, oslot = h0.y & 0xffffu, tmask = h0.z, emask = h0.w;
+                    int oi = 0;
+                    if (oslot != 0xffffu) {
+                        oi = s_outer[oslot];
+                        if (oi < 0) continue;                       // outer control not satisfied by this tile
+                    }
+                    if ((base & tmask) != tmask) continue;          // tile-local control outside the registers
+                    switch (code) {
+#define QJ_D1C(A) op_dense1<T, A, false>(x, pay, emask)
+#define QJ_D1R(A) op_dense1<T, A, true>(x, pay, emask)
+#define QJ_P1(A) op_perm1<T, A>(x, emask)
+#define QJ_D2(A, B) op_dense2<T, A, B>(x, pay, emask)
+#define QJ_P2(A, B) op_perm2<T, A, B>(x, emask)
+                        QJ_SLOT_CASES(C_DENSE1C, QJ_D1C)
+                        QJ_SLOT_CASES(C_DENSE1R, QJ_D1R)
+                        QJ_SLOT_CASES(C_PERM1, QJ_P1)
+                        QJ_PAIR_CASES(C_DENSE2, QJ_D2)
+                        QJ_PAIR_CASES(C_PERM2, QJ_P2)
+#undef QJ_D1C
+#undef QJ_D1R
+#undef QJ_P1
+#undef QJ_D2
+#undef QJ_P2
+                        case C_DIAGC: {
+                            T ph[16 / sizeof(T)];
+                            load_units<1>(pay, ph);
+                            mul_masked<T>(x, emask, ph[0], ph[1]);
+                        } break;
+                        case C_SIGNC:
+                            flip_masked<T>(x, emask, 0x80000000u);
+                            break;
+                        case C_DIAG1:
+                        case C_SIGN1: {
+                            const int nf = int(h0.y >> 16);
+                            int idx = oi;
+                            if (nf > 0) idx |= field_of(base, h1.y);
+                            if (nf > 1) idx |= field_of(base, h1.z);
+                            if (nf > 2) idx |= field_of(base, h1.w);
+                            if (nf > 3) {
+                                const uint4 f = pay[0];
+                                idx |= field_of(base, f.x);
+                                if (nf > 4) idx |= field_of(base, f.y);
+                                if (nf > 5) idx |= field_of(base, f.z);
+                                if (nf > 6) idx |= field_of(base, f.w);
+                            }
+                            const Cx<T> ph = ldg_cx(tables + h1.x + idx);
+                            if (code == C_SIGN1) flip_masked<T>(x, emask, sign_of(ph.re));
+                            else mul_masked<T>(x, emask, ph.re, ph.im);
+                        } break;
+                        default: {  // C_DIAGN: table index = outer part | fields of the base | element part
+                            const int nf = int(h0.y >> 16);
+                            const uint4 f = pay[0], w = pay[1];
+                            int idxb = oi;
+                            if (nf > 0) idxb |= field_of(base, h1.y);
+                            if (nf > 1) idxb |= field_of(base, h1.z);
+                            if (nf > 2) idxb |= field_of(base, h1.w);
+                            if (nf > 3) idxb |= field_of(base, f.x);
+                            if (nf > 4) idxb |= field_of(base, f.y);
+                            if (nf > 5) idxb |= field_of(base, f.z);
+                            if (nf > 6) idxb |= field_of(base, f.w);
+                            const int w0 = int(w.x & 0xffffu), w1 = int(w.x >> 16), w2 = int(w.y & 0xffffu),
+                                      w3 = int(w.y >> 16), w4 = int(w.z & 0xffffu);
+                            const Cx<T> *tab = tables + h1.x;
+#pragma unroll
+                            for (int e8 = 0; e8 < N; e8 += 8) {  // eight gathers in flight before the first multiply
+                                Cx<T> ph[8];
+#pragma unroll
+                                for (int k = 0; k < 8; k++) {
+                                    const int e = e8 + k;
+                                    const int idx = idxb | ((e & 1) ? w0 : 0) | ((e & 2) ? w1 : 0) | ((e & 4) ? w2 : 0) |
+                                                    ((e & 8) ? w3 : 0) | ((e & 16) ? w4 : 0);
+                                    ph[k].re = T(1); ph[k].im = T(0);
+                                    if ((emask >> e) & 1u) ph[k] = ldg_cx(tab + idx);
+                                }
+#pragma unroll
+                                for (int k = 0; k < 8; k++) {
+                                    const int e = e8 + k;
+                                    if (!((emask >> e) & 1u)) continue;
+                                    const Cx<T> v = x[e];
+                                    x[e].re = fma(ph[k].re, v.re, -ph[k].im * v.im);
+                                    x[e].im = fma(ph[k].re, v.im, ph[k].im * v.re);
+                                }
+                            }
+                        }
+                    }
+                }
+
+#pragma unroll
+                for (int v = 0; v < 16; v++) {
+                    const uint32_t off = S ^ ((v & 1) ? vd[0] : 0u) ^ ((v & 2) ? vd[1] : 0u) ^
+                                         ((v & 4) ? vd[2] : 0u) ^ ((v & 8) ? vd[3] : 0u);
+                    uint4 q;
+                    if constexpr (sizeof(T) == 8) {
+                        q.x = uint32_t(__double2loint(x[v].re)); q.y = uint32_t(__double2hiint(x[v].re));
+                        q.z = uint32_t(__double2loint(x[v].im)); q.w = uint32_t(__double2hiint(x[v].im));
+                    } else {
+                        q.x = __float_as_uint(x[2 * v].re); q.y = __float_as_uint(x[2 * v].im);
+                        q.z = __float_as_uint(x[2 * v + 1].re); q.w = __float_as_uint(x[2 * v + 1].im);
+                    }
+                    *reinterpret_cast<uint4 *>(smem_raw + off) = q;
+                }
+            }
+            __syncthreads();
+        }
+
+        // ---- store the tile
+        constexpr int UNR = 8;
+        for (int v0 = 0; v0 < nvec; v0 += kThreads * UNR) {
+            uint4 q[UNR];
+#pragma unroll
+            for (int u = 0; u < UNR; u++) {
+                const int lv = v0 + u * kThreads + tid;
+                if (lv < nvec) q[u] = tilev[swz_vec(uint32_t(lv))];
+            }
+#pragma unroll
+            for (int u = 0; u < UNR; u++) {
+                const int lv = v0 + u * kThreads + tid;
+                if (lv < nvec) gvec[base_vec + s_runoff[lv >> rv] + (lv & rvmask)] = q[u];
+            }
+        }
+        __syncthreads();   // the next tile's asynchronous copies overwrite the buffer
+    }
+}
+
+// ------------------------------------------------------------------ host-side encoding
+typedef std::complex<double> cd;
+
+template <typename T>
+cd load_cx(const unsigned char *p, int64_t i) {
+    const T *t = reinterpret_cast<const T *>(p);
+    return cd(double(t[2 * i]), double(t[2 * i + 1]));
+}
+
+struct Unit {
+    uint32_t w[4];
+};
+
+struct Encoder {
+    int dtype;
+    size_t esz;
+    const unsigned char *hdata;
+    int64_t ndata;
+    std::vector<unsigned char> tables;   // device phase tables, state dtype
+
+    cd data_at(int64_t off) const {
+        return dtype == QJ_C128 ? load_cx<double>(hdata, off) : load_cx<float>(hdata, off);
+    }
+    uint32_t push_table(const std::vector<cd> &t) {
+        const uint32_t off = uint32_t(tables.size() / esz);
+        const size_t at = tables.size();
+        tables.resize(at + t.size() * esz);
+        for (size_t i = 0; i < t.size(); i++) {
+            if (dtype == QJ_C128) {
+                double *d = reinterpret_cast<double *>(tables.data() + at) + 2 * i;
+                d[0] = t[i].real(); d[1] = t[i].imag();
+            } else {
+                float *d = reinterpret_cast<float *>(tables.data() + at) + 2 * i;
+                d[0] = float(t[i].real()); d[1] = float(t[i].imag());
+            }
+        }
+        return off;
+    }
+    // scalars (state precision) appended to a unit stream
+    void push_scalars(std::vector<Unit> &out, const std::vector<double> &s) const {
+        std::vector<unsigned char> raw;
+        if (dtype == QJ_C128) {
+            raw.resize(s.size() * 8);
+            memcpy(raw.data(), s.data(), raw.size());
+        } else {
+            raw.resize(s.size() * 4);
+            for (size_t i = 0; i < s.size(); i++) {
+                const float f = float(s[i]);
+                memcpy(raw.data() + 4 * i, &f, 4);
+            }
+        }
+        raw.resize((raw.size() + 15) / 16 * 16, 0);
+        for (size_t i = 0; i < raw.size(); i += 16) {
+            Unit u;
+            memcpy(u.w, raw.data() + i, 16);
+            out.push_back(u);
+        }
+    }
+};
+
+inline int pair_index(int a, int b) { return b * (b - 1) / 2 + a; }
+
+}  // namespace
+}  // namespace qj
+
+struct qj_program {
+    int dtype = 0;
+    int nqubits = 0;
+    struct Launch {
+        qj::PassGeom geom;
+        int64_t blob_off = 0;   // units into d_blob
+        size_t smem = 0;
+        int nrounds = 0, nops = 0;
+    };
+    std::vector<Launch> launches;
+    void *d_blob = nullptr;
+    void *d_tables = nullptr;
+    int64_t total_mops = 0, total_rounds = 0;
+};
+
+using namespace qj;
+
+extern "C" int qj_program_create(qj_handle *h, int dtype, int nqubits, const qj_pass_desc *passes,
+                                 int npasses, const qj_round_desc *rounds_in, int64_t nrounds_in,
+                                 const qj_op_desc *ops, int64_t nops, const void *data, int64_t ndata,
+                                 qj_program **out) {
+    QJ_REQUIRE(h && out && (passes || npasses == 0), "null argument");
+    QJ_REQUIRE(dtype == QJ_C64 || dtype == QJ_C128, "dtype must be QJ_C64 or QJ_C128");
+    QJ_REQUIRE(nqubits >= kMinTileBits && nqubits <= QJ_MAX_QUBITS, "tile programs need 6 <= nqubits <= QJ_MAX_QUBITS");
+    QJ_REQUIRE(npasses >= 0 && nrounds_in >= 0 && nops >= 0 && ndata >= 0, "negative count");
+    QJ_REQUIRE((rounds_in || nrounds_in == 0) && (ops || nops == 0) && (data || ndata == 0), "null argument");
+
+    const int VS = (dtype == QJ_C128) ? 0 : 1;
+    const int J = (dtype == QJ_C128) ? 4 : 5;
+    const int N = 1 << J;
+    Encoder enc;
+    enc.dtype = dtype;
+    enc.esz = (dtype == QJ_C128) ? 16 : 8;
+    enc.hdata = static_cast<const unsigned char *>(data);
+    enc.ndata = ndata;
+
+    auto *prog = new qj_program();
+    prog->dtype = dtype;
+    prog->nqubits = nqubits;
+    std::vector<Unit> blob_all;
+    auto bail = [&](const std::string &msg) {
+        delete prog;
+        return fail(QJ_ERR_INVALID, msg);
+    };
+
+    for (int pi = 0; pi < npasses; pi++) {
+        const qj_pass_desc &pd = passes[pi];
+        const int T = pd.nlocal;
+        if (T < kMinTileBits || T - VS > kMaxTileVecBits || T > nqubits)
+            return bail("pass: need 6 <= nlocal <= min(12 (complex128) / 13 (complex64), nqubits)");
+        int lpos[QJ_MAX_QUBITS];
+        for (int b = 0; b < QJ_MAX_QUBITS; b++) lpos[b] = -1;
+        for (int i = 0; i < T; i++) {
+            const int b = pd.local_bits[i];
+            if (b < 0 || b >= nqubits) return bail("pass: local bit out of range");
+            if (i && b <= pd.local_bits[i - 1]) return bail("pass: local bits must be strictly ascending");
+            lpos[b] = i;
+        }
+        int r = 0;
+        while (r < T && pd.local_bits[r] == r) r++;
+        if (r < 1) return bail("pass: the tile must contain index bit 0");
+        if (T - r > kMaxHiBits) return bail("pass: too many local bits above the contiguous run");
+        if (pd.first_round < 0 || pd.nrounds < 0 || pd.first_round + pd.nrounds > nrounds_in)
+            return bail("pass: round range out of bounds");
+
+        PassGeom geo;
+        memset(&geo, 0, sizeof(geo));
+        geo.T = T; geo.r = r; geo.nh = T - r;
+        for (int i = r; i < T; i++) {
+            geo.hibit[i - r] = pd.local_bits[i];
+            geo.pos[i - r] = pd.local_bits[i] - r;
+        }
+        geo.npos = T - r;
+        geo.ntiles = int64_t(1) << (nqubits - T);
+        const int Tv = T - VS;
+
+        // one launch = the rounds whose image fits the shared-memory budget
+        std::vector<Unit> round_units, outer_units, op_units;
+        int launch_rounds = 0, launch_ops = 0;
+        auto close_launch = [&]() {
+            if (launch_rounds == 0) return;
+            std::vector<Unit> img;
+            Unit hdr;
+            const uint32_t off_rounds = 1, off_outer = off_rounds + uint32_t(round_units.size());
+            const uint32_t off_ops = off_outer + uint32_t(outer_units.size());
+            hdr.w[0] = uint32_t(launch_rounds); hdr.w[1] = uint32_t(outer_units.size() / 2);
+            hdr.w[2] = off_rounds; hdr.w[3] = off_outer;
+            img.push_back(hdr);
+            for (size_t i = 0; i < round_units.size(); i += 3) round_units[i].w[0] += off_ops;   // first_unit
+            img.insert(img.end(), round_units.begin(), round_units.end());
+            img.insert(img.end(), outer_units.begin(), outer_units.end());
+            img.insert(img.end(), op_units.begin(), op_units.end());
+            qj_program::Launch L;
+            L.geom = geo;
+            L.geom.blob_units = int(img.size());
+            L.blob_off = int64_t(blob_all.size());
+            L.nrounds = launch_rounds;
+            L.nops = launch_ops;
+            L.smem = (size_t(1) << Tv) * 16 + img.size() * 16 + (size_t(8) << geo.nh) + (outer_units.size() / 2) * 4 + 16;
+            prog->launches.push_back(L);
+            blob_all.insert(blob_all.end(), img.begin(), img.end());
+            round_units.clear(); outer_units.clear(); op_units.clear();
+            launch_rounds = 0; launch_ops = 0;
+        };
+
+        for (int64_t ri = pd.first_round; ri < pd.first_round + pd.nrounds; ri++) {
+            const qj_round_desc &rdesc = rounds_in[ri];
+            if (rdesc.nreg != J) return bail("round: need 4 (complex128) / 5 (complex64) register bits");
+            if (rdesc.first_op < 0 || rdesc.nops < 0 || rdesc.first_op + rdesc.nops > nops)
+                return bail("round: op range out of bounds");
+            // register slots: slot j <-> local position rp[j] (ascending)
+            int rp[8];
+            int slot_of_pos[QJ_MAX_LOCAL_BITS];
+            for (int i = 0; i < QJ_MAX_LOCAL_BITS; i++) slot_of_pos[i] = -1;
+            for (int j = 0; j < J; j++) {
+                const int b = rdesc.reg_bits[j];
+                if (b < 0 || b >= nqubits || lpos[b] < 0) return bail("round: register bit is not a local bit of its pass");
+                if (j && b <= rdesc.reg_bits[j - 1]) return bail("round: register bits must be strictly ascending");
+                rp[j] = lpos[b];
+                slot_of_pos[rp[j]] = j;
+            }
+            if (VS && rp[0] != 0) return bail("round: complex64 rounds must keep index bit 0 in registers");
+            // vector positions of the register slots and of the thread bits
+            bool is_regvec[kMaxTileVecBits + 1] = {false};
+            uint32_t vd[4];
+            for (int j = VS; j < J; j++) {
+                const int q = rp[j] - VS;
+                is_regvec[q] = true;
+                vd[j - VS] = swz_vec(1u << q) << 4;
+            }
+            std::vector<int> tq;      // thread bit k <-> vector position tq[k]
+            {
+                bool used_res[3] = {false, false, false};
+                std::vector<int> freeq;
+                for (int q = 0; q < Tv; q++) if (!is_regvec[q]) freeq.push_back(q);
+                std::vector<bool> picked(freeq.size(), false);
+                for (size_t i = 0; i < freeq.size() && tq.size() < 3; i++) {
+                    if (!used_res[freeq[i] % 3]) {
+                        used_res[freeq[i] % 3] = true;
+                        picked[i] = true;
+                        tq.push_back(freeq[i]);
+                    }
+                }
+                for (size_t i = 0; i < freeq.size(); i++) if (!picked[i]) tq.push_back(freeq[i]);
+            }
+            uint32_t regmask = 0;     // local positions held in registers
+            for (int j = 0; j < J; j++) regmask |= 1u << rp[j];
+
+            // would this round overflow the image?  (conservative: close before encoding)
+            std::vector<Unit> r_ops;
+            std::vector<Unit> r_outer;
+            int r_nops = 0;
+            const int outer_base = int(outer_units.size() / 2);
+
+            auto elem_bits = [&](int e) {   // local positions set in element e
+                uint32_t o = 0;
+                for (int j = 0; j < J; j++) if ((e >> j) & 1) o |= 1u << rp[j];
+                return o;
+            };
+            auto add_outer = [&](const HostOuter &ho) -> int {
+                if (ho.ocmask == 0 && ho.nbits == 0) return 0xffff;
+                Unit u0, u1;
+                memset(&u0, 0, sizeof(u0)); memset(&u1, 0, sizeof(u1));
+                u0.w[0] = uint32_t(ho.ocmask); u0.w[1] = uint32_t(ho.ocmask >> 32); u0.w[2] = uint32_t(ho.nbits);
+                uint32_t srcw[3] = {0, 0, 0}, dstw[2] = {0, 0};
+                for (int b = 0; b < ho.nbits; b++) {
+                    srcw[b >> 2] |= uint32_t(ho.src[b]) << ((b & 3) * 8);
+                    dstw[b >> 3] |= uint32_t(ho.dst[b]) << ((b & 7) * 4);
+                }
+                u0.w[3] = srcw[0]; u1.w[0] = srcw[1]; u1.w[1] = srcw[2]; u1.w[2] = dstw[0]; u1.w[3] = dstw[1];
+                r_outer.push_back(u0); r_outer.push_back(u1);
+                return outer_base + int(r_outer.size() / 2) - 1;
+            };
+            auto push_op = [&](uint32_t code, int oslot, int nfields, uint32_t tmask, uint32_t emask, uint32_t table,
+                               const uint32_t *fields, const std::vector<Unit> &payload) {
+                Unit h0, h1;
+                h0.w[0] = code | (uint32_t(2 + payload.size()) << 16);
+                h0.w[1] = uint32_t(oslot) | (uint32_t(nfields) << 16);
+                h0.w[2] = tmask; h0.w[3] = emask;
+                h1.w[0] = table;
+                h1.w[1] = fields ? fields[0] : 0; h1.w[2] = fields ? fields[1] : 0; h1.w[3] = fields ? fields[2] : 0;
+                r_ops.push_back(h0); r_ops.push_back(h1);
+                r_ops.insert(r_ops.end(), payload.begin(), payload.end());
+                r_nops++;
+            };
+
+            for (int64_t oi = rdesc.first_op; oi < rdesc.first_op + rdesc.nops; oi++) {
+                const qj_op_desc &od = ops[oi];
+                if (od.ncontrols < 0 || od.ncontrols > QJ_MAX_QUBITS) return bail("op: bad control count");
+                uint64_t seen = 0;
+                uint32_t lcmask = 0;          // local control positions
+                HostOuter ho;
+                for (int c = 0; c < od.ncontrols; c++) {
+                    const int b = od.controls[c];
+                    if (b < 0 || b >= nqubits) return bail("op: control bit out of range");
+                    if ((seen >> b) & 1) return bail("op: duplicate qubit");
+                    seen |= uint64_t(1) << b;
+                    if (lpos[b] >= 0) lcmask |= 1u << lpos[b];
+                    else ho.ocmask |= uint64_t(1) << b;
+                }
+                const uint32_t tmask = lcmask & ~regmask;
+                const uint32_t rcmask = lcmask & regmask;
+                uint32_t cmask_e = 0;         // elements that satisfy the register-slot controls
+                for (int e = 0; e < N; e++) if ((elem_bits(e) & rcmask) == rcmask) cmask_e |= 1u << e;
+
+                if (od.kind == QJ_OPK_DENSE1 || od.kind == QJ_OPK_DENSE2) {
+                    const int nt = (od.kind == QJ_OPK_DENSE1) ? 1 : 2;
+                    if (od.ntargets != nt) return bail("op: dense target count mismatch");
+                    const int64_t need = (nt == 1) ? 4 : 16;
+                    if (od.data_offset < 0 || od.data_offset + need > ndata) return bail("op: matrix outside the data array");
+                    int sl[2] = {0, 0};
+                    for (int t = 0; t < nt; t++) {
+                        const int b = od.targets[t];
+                        if (b < 0 || b >= nqubits) return bail("op: target bit out of range");
+                        if ((seen >> b) & 1) return bail("op: duplicate qubit");
+                        seen |= uint64_t(1) << b;
+                        if (lpos[b] < 0) return bail("op: dense target is not a local bit of its pass");
+                        if (slot_of_pos[lpos[b]] < 0) return bail("op: dense target is not a register bit of its round");
+                        sl[t] = slot_of_pos[lpos[b]];
+                    }
+                    const int oslot = add_outer(ho);
+                    std::vector<cd> m(need);
+                    for (int64_t i = 0; i < need; i++) m[i] = enc.data_at(od.data_offset + i);
+                    std::vector<Unit> payload;
+                    if (nt == 1) {
+                        bool real = true;
+                        for (const cd &z : m) real = real && z.imag() == 0.0;
+                        const bool is_x = real && m[0] == 0.0 && m[1] == 1.0 && m[2] == 1.0 && m[3] == 0.0;
+                        if (is_x) {
+                            push_op(C_PERM1 + sl[0], oslot, 0, tmask, cmask_e, 0, nullptr, payload);
+                        } else if (real) {
+                            enc.push_scalars(payload, {m[0].real(), m[1].real(), m[2].real(), m[3].real()});
+                            push_op(C_DENSE1R + sl[0], oslot, 0, tmask, cmask_e, 0, nullptr, payload);
+                        } else {
+                            std::vector<double> s;
+                            for (const cd &z : m) { s.push_back(z.real()); s.push_back(z.imag()); }
+                            enc.push_scalars(payload, s);
+                            push_op(C_DENSE1C + sl[0], oslot, 0, tmask, cmask_e, 0, nullptr, payload);
+                        }
+                    } else {
+                        int a = sl[0], b = sl[1];
+                        if (a > b) {  // canonical slot order: exchange the matrix-index bits
+                            std::vector<cd> t(16);
+                            auto sw = [](int i) { return ((i & 1) << 1) | (i >> 1); };
+                            for (int i = 0; i < 4; i++)
+                                for (int j = 0; j < 4; j++) t[sw(i) * 4 + sw(j)] = m[i * 4 + j];
+                            m = t;
+                            std::swap(a, b);
+                        }
+                        static const double swap_m[16] = {1, 0, 0, 0, 0, 0, 1, 0, 0, 1, 0, 0, 0, 0, 0, 1};
+                        bool is_swap = true;
+                        for (int i = 0; i < 16; i++) is_swap = is_swap && m[i] == cd(swap_m[i]);
+                        if (is_swap) {
+                            push_op(C_PERM2 + pair_index(a, b), oslot, 0, tmask, cmask_e, 0, nullptr, payload);
+                        } else {
+                            std::vector<double> s;
+                            for (const cd &z : m) { s.push_back(z.real()); s.push_back(z.imag()); }
+                            enc.push_scalars(payload, s);
+                            push_op(C_DENSE2 + pair_index(a, b), oslot, 0, tmask, cmask_e, 0, nullptr, payload);
+                        }
+                    }
+                } else if (od.kind == QJ_OPK_DIAG) {
+                    const int nb = od.ntargets;
+                    if (nb < 0 || nb > QJ_MAX_DIAG_BITS) return bail("op: diagonal table over too many bits");
+                    if (od.data_offset < 0 || od.data_offset + (int64_t(1) << nb) > ndata) return bail("op: table outside the data array");
+                    // classify the table bits
+                    std::vector<int> regj, regslot;        // table bit -> register slot
+                    std::vector<std::pair<int, int>> thr;  // (local position, table bit)
+                    std::vector<std::pair<int, int>> outb; // (index bit, table bit)
+                    for (int j = 0; j < nb; j++) {
+                        const int b = od.targets[j];
+                        if (b < 0 || b >= nqubits) return bail("op: table bit out of range");
+                        if ((seen >> b) & 1) return bail("op: duplicate qubit");
+                        seen |= uint64_t(1) << b;
+                        if (lpos[b] < 0) outb.push_back({b, j});
+                        else if (slot_of_pos[lpos[b]] >= 0) { regj.push_back(j); regslot.push_back(slot_of_pos[lpos[b]]); }
+                        else thr.push_back({lpos[b], j});
+                    }
+                    std::sort(thr.begin(), thr.end());
+                    std::sort(outb.begin(), outb.end());
+                    const int nthr = int(thr.size()), nout = int(outb.size()), k = int(regj.size());
+                    if (nout > 11) return bail("op: diagonal table over more than 11 bits outside the tile");
+                    // thread fields: runs of consecutive local positions
+                    uint32_t fields[8] = {0};
+                    int nf = 0;
+                    for (int i = 0; i < nthr; i++) {
+                        if (nf > 0) {
+                            const uint32_t fl = fields[nf - 1];
+                            const int src = fl & 255, len = (fl >> 8) & 255;
+                            if (src + len == thr[i].first) { fields[nf - 1] = fl + (1u << 8); continue; }
+                        }
+                        if (nf == 7) return bail("op: diagonal table needs too many bit fields");
+                        fields[nf++] = uint32_t(thr[i].first) | (1u << 8) | (uint32_t(i) << 16);
+                    }
+                    for (int i = 0; i < nout; i++) {
+                        ho.src[i] = uint8_t(outb[i].first);
+                        ho.dst[i] = uint8_t(nthr + i);
+                    }
+                    ho.nbits = nout;
+                    const int nsub = nthr + nout;
+                    auto sub_index = [&](int s, int a) {   // sub-table index s, register assignment a -> host table index
+                        int idx = 0;
+                        for (int i = 0; i < nthr; i++) idx |= ((s >> i) & 1) << thr[i].second;
+                        for (int i = 0; i < nout; i++) idx |= ((s >> (nthr + i)) & 1) << outb[i].second;
+                        for (int i = 0; i < k; i++) idx |= ((a >> i) & 1) << regj[i];
+                        return idx;
+                    };
+                    // slices along the register bits
+                    struct Slice { int a; std::vector<cd> t; bool sign; };
+                    std::vector<Slice> slices;
+                    for (int a = 0; a < (1 << k); a++) {
+                        Slice sl;
+                        sl.a = a;
+                        sl.t.resize(size_t(1) << nsub);
+                        bool ident = true, sign = true;
+                        for (int s = 0; s < (1 << nsub); s++) {
+                            const cd z = enc.data_at(od.data_offset + sub_index(s, a));
+                            sl.t[s] = z;
+                            ident = ident && z == cd(1.0);
+                            sign = sign && z.imag() == 0.0 && (z.real() == 1.0 || z.real() == -1.0);
+                        }
+                        sl.sign = sign;
+                        if (!ident) slices.push_back(sl);
+                    }
+                    if (slices.empty()) continue;
+                    const bool use_slices = k <= 2 || slices.size() <= 4;
+                    const int oslot = add_outer(ho);
+                    std::vector<Unit> payload;
+                    if (use_slices) {
+                        for (const Slice &sl : slices) {
+                            uint32_t emask = 0;
+                            for (int e = 0; e < N; e++) {
+                                bool ok = (cmask_e >> e) & 1u;
+                                for (int i = 0; i < k && ok; i++) ok = ((e >> regslot[i]) & 1) == ((sl.a >> i) & 1);
+                                if (ok) emask |= 1u << e;
+                            }
+                            payload.clear();
+                            if (nsub == 0) {
+                                if (sl.sign) {
+                                    push_op(C_SIGNC, oslot, 0, tmask, emask, 0, nullptr, payload);
+                                } else {
+                                    enc.push_scalars(payload, {sl.t[0].real(), sl.t[0].imag()});
+                                    push_op(C_DIAGC, oslot, 0, tmask, emask, 0, nullptr, payload);
+                                }
+                                continue;
+                            }
+                            if (nf > 3) {
+                                Unit u;
+                                for (int i = 0; i < 4; i++) u.w[i] = fields[3 + i];
+                                payload.push_back(u);
+                            }
+                            push_op(sl.sign ? C_SIGN1 : C_DIAG1, oslot, nf, tmask, emask, enc.push_table(sl.t), fields, payload);
+                        }
+                    } else {
+                        // general table: index = thread fields | outer bits | register bits
+                        std::vector<cd> t(size_t(1) << nb);
+                        for (int a = 0; a < (1 << k); a++)
+                            for (int s = 0; s < (1 << nsub); s++)
+                                t[size_t(a) << nsub | s] = enc.data_at(od.data_offset + sub_index(s, a));
+                        Unit uf, uw;
+                        memset(&uf, 0, sizeof(uf)); memset(&uw, 0, sizeof(uw));
+                        for (int i = 0; i < 4; i++) uf.w[i] = fields[3 + i];
+                        uint16_t w[8] = {0};
+                        for (int i = 0; i < k; i++) w[regslot[i]] = uint16_t(1u << (nsub + i));
+                        uw.w[0] = w[0] | (uint32_t(w[1]) << 16); uw.w[1] = w[2] | (uint32_t(w[3]) << 16); uw.w[2] = w[4];
+                        payload.push_back(uf); payload.push_back(uw);
+                        push_op(C_DIAGN, oslot, nf, tmask, cmask_e, enc.push_table(t), fields, payload);
+                    }
+                } else {
+                    return bail("op: unknown kind");
+                }
+            }
+
+            // append the round (closing the launch first when the image would overflow)
+            const size_t need_units = 1 + round_units.size() + 3 + outer_units.size() + r_outer.size() + op_units.size() + r_ops.size();
+            if (3 + r_outer.size() + r_ops.size() + 1 > size_t(kMaxBlobUnits) || r_outer.size() / 2 > size_t(kMaxOuter))
+                return bail("round: too many ops for one round");
+            if (need_units > size_t(kMaxBlobUnits) || (outer_units.size() + r_outer.size()) / 2 > size_t(kMaxOuter)) {
+                // the outer slots of this round were numbered relative to the open launch: renumber
+                close_launch();
+                for (size_t i = 0; i < r_ops.size();) {
+                    const uint32_t units = r_ops[i].w[0] >> 16;
+                    const uint32_t oslot = r_ops[i].w[1] & 0xffffu;
+                    if (oslot != 0xffffu) r_ops[i].w[1] = (r_ops[i].w[1] & 0xffff0000u) | (oslot - uint32_t(outer_base));
+                    i += units;
+                }
+            }
+            if (r_nops > 0) {
+                Unit u0, u1, u2;
+                memset(&u0, 0, sizeof(u0)); memset(&u1, 0, sizeof(u1)); memset(&u2, 0, sizeof(u2));
+                u0.w[0] = uint32_t(op_units.size());   // relative to the op stream; rebased in close_launch
+                u0.w[1] = uint32_t(r_nops);
+                u0.w[2] = vd[0] | (vd[1] << 16); u0.w[3] = vd[2] | (vd[3] << 16);
+                for (size_t kbit = 0; kbit < tq.size() && kbit < 8; kbit++) {
+                    const uint32_t td = swz_vec(1u << tq[kbit]) << 4;
+                    u1.w[kbit >> 1] |= td << ((kbit & 1) * 16);
+                    u2.w[kbit >> 2] |= uint32_t(tq[kbit] + VS) << ((kbit & 3) * 8);
+                }
+                round_units.push_back(u0); round_units.push_back(u1); round_units.push_back(u2);
+                outer_units.insert(outer_units.end(), r_outer.begin(), r_outer.end());
+                op_units.insert(op_units.end(), r_ops.begin(), r_ops.end());
+                launch_rounds++;
+                launch_ops += r_nops;
+                prog->total_rounds++;
+                prog->total_mops += r_nops;
+            }
+        }
+        close_launch();
+    }
+
+    cudaSetDevice(h->device);
+    auto upload = [&](void **dst, const void *src, size_t bytes) -> cudaError_t {
+        if (bytes == 0) bytes = 16;   // never hand a null table pointer to the kernel
+        cudaError_t e = cudaMalloc(dst, bytes);
+        if (e != cudaSuccess || src == nullptr) return e;
+        return cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, h->stream);
+    };
+    cudaError_t e = upload(&prog->d_blob, blob_all.empty() ? nullptr : blob_all.data(), blob_all.size() * 16);
+    if (e == cudaSuccess) e = upload(&prog->d_tables, enc.tables.empty() ? nullptr : enc.tables.data(), enc.tables.size());
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);  // host vectors die with this frame
+    if (e != cudaSuccess) {
+        qj_program_destroy(h, prog);
+        return fail(QJ_ERR_CUDA, std::string("program upload: ") + cudaGetErrorString(e));
+    }
+    *out = prog;
+    return QJ_OK;
+}
+
+extern "C" int qj_program_destroy(qj_handle *h, qj_program *p) {
+    if (!p) return QJ_OK;
+    if (h) {
+        cudaSetDevice(h->device);
+        cudaStreamSynchronize(h->stream);
+    }
+    cudaFree(p->d_blob);
+    cudaFree(p->d_tables);
+    delete p;
+    return QJ_OK;
+}
+
+extern "C" int qj_program_stats(const qj_program *p, int64_t *nlaunches, int64_t *nrounds, int64_t *nmops) {
+    QJ_REQUIRE(p != nullptr, "null program");
+    if (nlaunches) *nlaunches = (int64_t)p->launches.size();
+    if (nrounds) *nrounds = p->total_rounds;
+    if (nmops) *nmops = p->total_mops;
+    return QJ_OK;
+}
+
+namespace {
+template <typename T>
+int launch_pass(qj_handle *h, const qj_program *p, void *state, const qj_program::Launch &L) {
+    static bool configured = false;
+    if (!configured) {
+        QJ_CUDA_OK(cudaFuncSetAttribute(k_pass<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 << 10));
+        configured = true;
+    }
+    // two CTAs per SM when the tile is large; small tiles: more CTAs per SM
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t(224) << 10) / (L.smem + 1024)));
+    const unsigned grid = (unsigned)std::min<int64_t>(L.geom.ntiles, int64_t(h->sm_count) * std::min(per_sm, 2));
+    k_pass<T><<<grid, kThreads, L.smem, h->stream>>>(
+        reinterpret_cast<Cx<T> *>(state), L.geom, reinterpret_cast<const uint4 *>(p->d_blob) + L.blob_off,
+        reinterpret_cast<const Cx<T> *>(p->d_tables));
+    h->launches++;
+    QJ_CUDA_OK(cudaGetLastError());
+    return QJ_OK;
+}
+
+int run_launches(qj_handle *h, const qj_program *p, void *state, int first, int count) {
+    for (int li = first; li < first + count; li++) {
+        const qj_program::Launch &L = p->launches[li];
+        const int rc = (p->dtype == QJ_C128) ? launch_pass<double>(h, p, state, L) : launch_pass<float>(h, p, state, L);
+        if (rc) return rc;
+    }
+    return QJ_OK;
+}
+}  // namespace
+
+extern "C" int qj_program_run(qj_handle *h, const qj_program *p, void *state) {
+    QJ_REQUIRE(h && p && state, "null argument");
+    QJ_REQUIRE((reinterpret_cast<uintptr_t>(state) & 15) == 0, "state must be 16-byte aligned");
+    return run_launches(h, p, state, 0, (int)p->launches.size());
+}
+
+extern "C" int qj_program_run_launch(qj_handle *h, const qj_program *p, void *state, int launch) {
+    QJ_REQUIRE(h && p && state, "null argument");
+    QJ_REQUIRE(launch >= 0 && launch < (int)p->launches.size(), "launch index out of range");
+    return run_launches(h, p, state, launch, 1);
+}

@@ -3,11 +3,20 @@
 Upstream, ``Backend.execute_circuit`` (qibo) and ``MultiGpuOps.apply_gates``
 (/root/reference/src/qibojit/backends/gpu.py:1467-1476) loop ``for gate in queue:
 apply_gate(...)``: one pass over the state per gate.  The per-gate kernels here already run at
-the HBM roofline, so the only way to make a circuit faster is fewer passes.  A *pass* keeps a
-set of T index bits "local" (resident in shared memory, always including the low contiguous run)
-and executes every gate whose non-diagonal targets are local; diagonal gates (Z, CZ, U1, CU1, RZ,
-...) and controls need no locality at all.  Consecutive diagonal gates are merged into phase
-tables over at most ``max_diag_bits`` index bits.
+the HBM roofline, so the only way to make a circuit faster is fewer passes.
+
+Three levels, all decided here on the host (pure Python, CPU-testable):
+
+* a **pass** keeps a set of T index bits "local" (one tile of 2^T amplitudes resident in shared
+  memory, always including the low contiguous run) and executes every gate whose non-diagonal
+  targets are local; diagonal gates (Z, CZ, U1, CU1, RZ, ...) and controls need no locality;
+* inside a pass the ops are grouped into **rounds**: each thread of the kernel gathers the
+  2^J amplitudes spanned by J "register" bits of the tile and applies every op of the round to
+  them, so dense targets of a round must be register bits of that round (gates that commute are
+  hoisted into the open round);
+* inside a round, diagonal gates are merged into phase **tables**, keyed by the set of register
+  bits they touch, so that the kernel can slice a table along its register bits into per-thread
+  constants (one table look-up per thread and slice).
 
 The arithmetic of every gate is unchanged (same 2x2 / 4x4 complex mat-vec as
 gates.py:16-38, 118-193; diagonal factors are multiplied together on the host in double
@@ -27,11 +36,15 @@ OP_DTYPE = np.dtype([
     ("targets", "<i4", (_capi.QJ_MAX_DIAG_BITS,)),
     ("controls", "<i4", (_capi.QJ_MAX_QUBITS,)),
 ])
+ROUND_DTYPE = np.dtype([
+    ("nreg", "<i4"), ("reserved", "<i4"), ("first_op", "<i8"), ("nops", "<i8"),
+    ("reg_bits", "<i4", (_capi.QJ_MAX_REG_BITS,)),
+])
 PASS_DTYPE = np.dtype([
-    ("nlocal", "<i4"), ("reserved", "<i4"), ("first_op", "<i8"), ("nops", "<i8"),
+    ("nlocal", "<i4"), ("reserved", "<i4"), ("first_round", "<i8"), ("nrounds", "<i8"),
     ("local_bits", "<i4", (_capi.QJ_MAX_LOCAL_BITS,)),
 ])
-assert OP_DTYPE.itemsize == 264 and PASS_DTYPE.itemsize == 88
+assert OP_DTYPE.itemsize == 264 and PASS_DTYPE.itemsize == 88 and ROUND_DTYPE.itemsize == 56
 
 # diagonal in the computational basis: no locality needed
 DIAGONAL_GATES = frozenset({
@@ -40,15 +53,16 @@ DIAGONAL_GATES = frozenset({
 
 DEFAULT_TILE_BITS = {"complex128": 12, "complex64": 13}
 DEFAULT_RUN_BITS = {"complex128": 5, "complex64": 6}
-MAX_TILE_BITS = {"complex128": 12, "complex64": 13}   # 64 KiB tiles, double-buffered per SM
+MAX_TILE_BITS = {"complex128": 12, "complex64": 13}   # 64 KiB tiles, two resident CTAs per SM
+REG_BITS = {"complex128": 4, "complex64": 5}          # register bits per round (complex64: bit 0 + 4)
 MAX_HI_BITS = 8
-MIN_QUBITS = 4
+MIN_QUBITS = 6
 
 
 class PlanOp:
     """One operation in index-bit space.  kind: 'dense' (1 or 2 targets), 'diag', 'raw'."""
 
-    __slots__ = ("kind", "targets", "controls", "data", "gate", "bits")
+    __slots__ = ("kind", "targets", "controls", "data", "gate", "bits", "tset", "dset")
 
     def __init__(self, kind, targets=(), controls=(), data=None, gate=None):
         self.kind = kind
@@ -57,6 +71,10 @@ class PlanOp:
         self.data = data
         self.gate = gate
         self.bits = frozenset(self.targets) | frozenset(self.controls)
+        # bits the op changes non-diagonally / bits it only reads (it commutes with any op that is
+        # diagonal on them)
+        self.tset = frozenset(self.targets) if kind == "dense" else frozenset()
+        self.dset = self.bits - self.tset
 
 
 def _is_diagonal(gate):
@@ -97,29 +115,29 @@ def _matrix_is_diagonal(u):
 def partition(ops, nqubits, tile_bits, run_bits):
     """Greedy partition of PlanOps into segments: ('pass', local_bits, [ops]) or ('raw', op)."""
     T = max(MIN_QUBITS, min(tile_bits, nqubits))
-    r = min(run_bits, T)
+    r = max(1, min(run_bits, T))
     if T - r > MAX_HI_BITS:
         r = T - MAX_HI_BITS
     segments = []
     remaining = list(ops)
-    allbits = frozenset(range(nqubits))
     while remaining:
         if remaining[0].kind == "raw":
             segments.append(("raw", remaining.pop(0)))
             continue
         local = set(range(r))
-        blocked = set()
+        blocked_t, blocked_d = set(), set()
         taken, rest = [], []
         for i, op in enumerate(remaining):
-            if len(blocked) == nqubits:
+            if len(blocked_t) == nqubits:
                 rest.extend(remaining[i:])
                 break
             if op.kind == "raw":
-                blocked = set(allbits)
+                blocked_t = set(range(nqubits))
                 rest.append(op)
                 continue
-            if blocked & op.bits:
-                blocked |= op.bits
+            if (op.tset & blocked_t) or (op.tset & blocked_d) or (op.dset & blocked_t):
+                blocked_t |= op.tset
+                blocked_d |= op.dset
                 rest.append(op)
                 continue
             if op.kind == "diag":
@@ -130,7 +148,8 @@ def partition(ops, nqubits, tile_bits, run_bits):
                 local |= need
                 taken.append(op)
             else:
-                blocked |= op.bits
+                blocked_t |= op.tset
+                blocked_d |= op.dset
                 rest.append(op)
         b = 0
         while len(local) < T:  # pad with the lowest free bits: longer contiguous runs
@@ -140,6 +159,47 @@ def partition(ops, nqubits, tile_bits, run_bits):
         segments.append(("pass", sorted(local), taken))
         remaining = rest
     return segments
+
+
+# ------------------------------------------------------------------------------- rounds
+def schedule_rounds(ops, local_bits, nreg, fixed=()):
+    """Ops of one pass -> [(reg_bits, [ops])]: every dense target of a round is one of its
+    `nreg` register bits (`fixed` bits are register bits of every round).  An op is hoisted into
+    the open round only over ops it commutes with, so non-commuting ops keep their order."""
+    rounds = []
+    remaining = list(ops)
+    fixed = set(fixed)
+    while remaining:
+        regs = set(fixed)
+        blocked_t, blocked_d = set(), set()
+        taken, rest = [], []
+        for op in remaining:
+            free = not ((op.tset & blocked_t) or (op.tset & blocked_d) or (op.dset & blocked_t))
+            if free and op.kind == "dense":
+                need = op.tset - regs
+                if len(regs) + len(need) <= nreg:
+                    regs |= need
+                else:
+                    free = False
+            if free:
+                taken.append(op)
+            else:
+                blocked_t |= op.tset
+                blocked_d |= op.dset
+                rest.append(op)
+        # pad with free local bits, preferably ones no diagonal op of the round touches (tables
+        # without register bits cost one look-up per thread), highest first
+        touched = set()
+        for op in taken:
+            touched |= op.dset
+        for pool in ([b for b in reversed(local_bits) if b not in touched], list(reversed(local_bits))):
+            for b in pool:
+                if len(regs) >= nreg:
+                    break
+                regs.add(b)
+        rounds.append((tuple(sorted(regs)), taken))
+        remaining = rest
+    return rounds
 
 
 class _DiagAcc:
@@ -166,8 +226,8 @@ class _DiagAcc:
             gi |= ((i >> self.bits.index(b)) & 1) << k
         self.table = self.table * otab[gi]
 
-    def finish(self, local_pos):
-        """-> PlanOp with control-like bits split off and table bits ordered by local position."""
+    def finish(self):
+        """-> PlanOp with control-like bits split off (None when the product is the identity)."""
         bits, table = list(self.bits), self.table
         controls = []
         j = 0
@@ -179,69 +239,70 @@ class _DiagAcc:
                 table = table[((i >> j) & 1) == 1]
             else:
                 j += 1
-        if not bits and not controls and table[0] == 1.0:
-            return None
-        if bits:
-            order = sorted(range(len(bits)), key=lambda k: (local_pos.get(bits[k], 1 << 20) , bits[k]))
-            if order != list(range(len(bits))):
-                t = table.reshape((2,) * len(bits))          # axis a <-> table bit len-1-a
-                axes = [len(bits) - 1 - order[len(bits) - 1 - a] for a in range(len(bits))]
-                table = np.ascontiguousarray(np.transpose(t, axes)).reshape(-1)
-                bits = [bits[k] for k in order]
-        if np.all(table == 1.0) and not controls:
+        if np.all(table == 1.0):
             return None
         return PlanOp("diag", tuple(bits), tuple(controls), table)
 
 
-def merge_diagonals(ops, local_bits, max_diag_bits):
-    """Merge commuting diagonal ops of one pass into phase tables (order-preserving w.r.t. every
-    dense op that targets one of their bits)."""
-    local_pos = {b: i for i, b in enumerate(local_bits)}
-    out, accs = [], []
+def merge_round_diagonals(ops, reg_bits, max_diag_bits):
+    """Merge the (mutually commuting) diagonal ops of one round into phase tables, one family of
+    tables per set of register bits touched; a dense op flushes the tables that touch its targets."""
+    regs = frozenset(reg_bits)
+    out, accs = [], []   # accs: [(signature, _DiagAcc)]
 
-    def flush(acc):
-        accs.remove(acc)
-        op = acc.finish(local_pos)
+    def flush(entry):
+        accs.remove(entry)
+        op = entry[1].finish()
         if op is not None:
             out.append(op)
 
     for op in ops:
         if op.kind == "diag":
+            sig = op.bits & regs
             obits = set(op.bits)
             best, best_key = None, None
-            for acc in accs:  # an open table that shares a bit with the op and has room for it
-                abits = set(acc.bits)
-                if not (obits & abits) or len(obits | abits) > max_diag_bits:
+            for entry in accs:
+                if entry[0] != sig:
+                    continue
+                abits = set(entry[1].bits)
+                if len(obits | abits) > max_diag_bits:
                     continue
                 key = (len(obits - abits), -len(obits & abits))
                 if best is None or key < best_key:
-                    best, best_key = acc, key
+                    best, best_key = entry, key
             if best is None:
-                best = _DiagAcc()
+                best = (sig, _DiagAcc())
                 accs.append(best)
-            best.absorb(op)
+            best[1].absorb(op)
             continue
-        for acc in [a for a in accs if set(a.bits) & set(op.targets)]:
-            flush(acc)
+        for entry in [e for e in accs if e[0] & op.tset]:
+            flush(entry)
         out.append(op)
-    for acc in list(accs):
-        flush(acc)
+    for entry in list(accs):
+        flush(entry)
     return out
 
 
-def plan_queue(queue, nqubits, matrices, tile_bits, run_bits, max_diag_bits=10):
-    """Gate queue -> [('pass', local_bits, [PlanOp]) | ('raw', gate)] (pure host logic)."""
+def plan_queue(queue, nqubits, matrices, tile_bits, run_bits, max_diag_bits=10, dtype="complex128"):
+    """Gate queue -> [('pass', local_bits, [(reg_bits, [PlanOp])]) | ('raw', gate)] (host logic)."""
     ops = []
     for gate in queue:
         ops.extend(lower_gate(gate, nqubits, matrices))
+    nreg = REG_BITS[str(dtype)]
+    fixed = (0,) if str(dtype) == "complex64" else ()
+    mdb = min(max_diag_bits, _capi.QJ_MAX_DIAG_BITS)
     out = []
     for seg in partition(ops, nqubits, tile_bits, run_bits):
         if seg[0] == "raw":
             out.append(("raw", seg[1].gate))
             continue
-        merged = merge_diagonals(seg[2], seg[1], min(max_diag_bits, _capi.QJ_MAX_DIAG_BITS))
-        if merged:
-            out.append(("pass", seg[1], merged))
+        rounds = []
+        for regs, rops in schedule_rounds(seg[2], seg[1], min(nreg, len(seg[1])), fixed):
+            merged = merge_round_diagonals(rops, regs, mdb)
+            if merged:
+                rounds.append((regs, merged))
+        if rounds:
+            out.append(("pass", seg[1], rounds))
     return out
 
 
@@ -258,14 +319,15 @@ class Program:
         self.tile_bits = min(int(tile_bits or DEFAULT_TILE_BITS[self.dtype]), MAX_TILE_BITS[self.dtype])
         self.run_bits = int(run_bits or DEFAULT_RUN_BITS[self.dtype])
         self.max_diag_bits = min(int(max_diag_bits), _capi.QJ_MAX_DIAG_BITS)
-        if self.nqubits < MIN_QUBITS:
-            raise ValueError(f"tile programs need at least {MIN_QUBITS} qubits")
         self.ngates = len(queue)
         self.segments = []       # ('program', handle, npasses) | ('raw', gate)
-        self.passes = []         # [(local_bits, [PlanOp])] for inspection
+        self.passes = []         # [(local_bits, [(reg_bits, [PlanOp])])] for inspection
+        if self.nqubits < MIN_QUBITS:   # too small for a tile: gate by gate
+            self.segments = [("raw", g) for g in queue]
+            return
         pending = []
         for seg in plan_queue(queue, self.nqubits, backend.custom_matrices, self.tile_bits,
-                              self.run_bits, self.max_diag_bits):
+                              self.run_bits, self.max_diag_bits, self.dtype):
             if seg[0] == "raw":
                 self._flush(pending)
                 pending = []
@@ -279,37 +341,45 @@ class Program:
         if not passes:
             return
         np_dtype = np.dtype(self.dtype)
-        nops = sum(len(p[1]) for p in passes)
+        nrounds = sum(len(p[1]) for p in passes)
+        nops = sum(len(r[1]) for p in passes for r in p[1])
         op_arr = np.zeros(nops, dtype=OP_DTYPE)
+        round_arr = np.zeros(nrounds, dtype=ROUND_DTYPE)
         pass_arr = np.zeros(len(passes), dtype=PASS_DTYPE)
-        chunks, offset, k = [], 0, 0
-        for pi, (local_bits, ops) in enumerate(passes):
+        chunks, offset, k, ri = [], 0, 0, 0
+        for pi, (local_bits, rounds) in enumerate(passes):
             pass_arr[pi]["nlocal"] = len(local_bits)
-            pass_arr[pi]["first_op"] = k
-            pass_arr[pi]["nops"] = len(ops)
+            pass_arr[pi]["first_round"] = ri
+            pass_arr[pi]["nrounds"] = len(rounds)
             pass_arr[pi]["local_bits"][:len(local_bits)] = local_bits
-            for op in ops:
-                rec = op_arr[k]
-                data = np.ascontiguousarray(np.asarray(op.data, dtype=np_dtype).reshape(-1))
-                if op.kind == "dense":
-                    rec["kind"] = _capi.QJ_OPK_DENSE1 if len(op.targets) == 1 else _capi.QJ_OPK_DENSE2
-                else:
-                    rec["kind"] = _capi.QJ_OPK_DIAG
-                rec["ntargets"] = len(op.targets)
-                rec["targets"][:len(op.targets)] = op.targets
-                rec["ncontrols"] = len(op.controls)
-                rec["controls"][:len(op.controls)] = op.controls
-                rec["data_offset"] = offset
-                chunks.append(data)
-                offset += data.size
-                k += 1
+            for regs, ops in rounds:
+                round_arr[ri]["nreg"] = len(regs)
+                round_arr[ri]["reg_bits"][:len(regs)] = regs
+                round_arr[ri]["first_op"] = k
+                round_arr[ri]["nops"] = len(ops)
+                ri += 1
+                for op in ops:
+                    rec = op_arr[k]
+                    data = np.ascontiguousarray(np.asarray(op.data, dtype=np_dtype).reshape(-1))
+                    if op.kind == "dense":
+                        rec["kind"] = _capi.QJ_OPK_DENSE1 if len(op.targets) == 1 else _capi.QJ_OPK_DENSE2
+                    else:
+                        rec["kind"] = _capi.QJ_OPK_DIAG
+                    rec["ntargets"] = len(op.targets)
+                    rec["targets"][:len(op.targets)] = op.targets
+                    rec["ncontrols"] = len(op.controls)
+                    rec["controls"][:len(op.controls)] = op.controls
+                    rec["data_offset"] = offset
+                    chunks.append(data)
+                    offset += data.size
+                    k += 1
         data = np.concatenate(chunks) if chunks else np.zeros(0, dtype=np_dtype)
         b = self.backend
         handle = ctypes.c_void_p()
         _capi.check(b._lib.qj_program_create(
             b._handle(), _capi.QJ_C128 if self.dtype == "complex128" else _capi.QJ_C64, self.nqubits,
-            pass_arr.ctypes.data, len(passes), op_arr.ctypes.data, nops, data.ctypes.data,
-            int(data.size), ctypes.byref(handle)))
+            pass_arr.ctypes.data, len(passes), round_arr.ctypes.data, nrounds, op_arr.ctypes.data, nops,
+            data.ctypes.data, int(data.size), ctypes.byref(handle)))
         self.segments.append(("program", handle, len(passes)))
         self.passes.extend(passes)
 

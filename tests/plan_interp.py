@@ -1,5 +1,6 @@
 """TEST INFRASTRUCTURE: numpy interpreter of planner PlanOps (qibojit_b200/planner.py), used to
-check the pass partition / diagonal merging on the CPU against gate-by-gate application."""
+check the pass partition / round schedule / diagonal merging on the CPU against gate-by-gate
+application."""
 
 import numpy as np
 
@@ -34,15 +35,20 @@ def apply_planop(state, op, nqubits):
     return out
 
 
-def run_plan(state, plan, nqubits, apply_raw):
+def run_plan(state, plan, nqubits, apply_raw, nreg=None, fixed=()):
     """plan: output of planner.plan_queue; apply_raw(state, gate) handles raw gates."""
     for seg in plan:
         if seg[0] == "raw":
             state = apply_raw(state, seg[1])
             continue
         local = set(seg[1])
-        for op in seg[2]:
-            if op.kind == "dense":
-                assert set(op.targets) <= local, "dense target outside the pass's local bits"
-            state = apply_planop(state, op, nqubits)
+        for regs, ops in seg[2]:
+            assert set(regs) <= local and list(regs) == sorted(set(regs)), "register bits must be local bits"
+            assert set(fixed) <= set(regs)
+            if nreg is not None:
+                assert len(regs) == nreg
+            for op in ops:
+                if op.kind == "dense":
+                    assert set(op.targets) <= set(regs), "dense target outside the round's register bits"
+                state = apply_planop(state, op, nqubits)
     return state

@@ -1,5 +1,5 @@
-"""CPU tests of the pass planner (host logic only): partition + diagonal merging must be a
-re-ordering of memory traffic, not of the circuit's meaning."""
+"""CPU tests of the pass planner (host logic only): partition + round schedule + diagonal merging
+must be a re-ordering of memory traffic, not of the circuit's meaning."""
 
 import numpy as np
 import pytest
@@ -19,13 +19,19 @@ def _raw(n):
     return apply_raw
 
 
+def _ops(plan):
+    return [op for seg in plan if seg[0] == "pass" for _, ops in seg[2] for op in ops]
+
+
+@pytest.mark.parametrize("dtype", ["complex128", "complex64"])
 @pytest.mark.parametrize("seed", range(6))
-@pytest.mark.parametrize("n,tile_bits,run_bits", [(6, 4, 2), (8, 5, 3), (9, 6, 2), (10, 10, 5), (7, 12, 5)])
-def test_plan_matches_gate_by_gate(n, tile_bits, run_bits, seed):
+@pytest.mark.parametrize("n,tile_bits,run_bits", [(6, 6, 2), (8, 6, 3), (9, 7, 2), (10, 10, 5), (7, 12, 5)])
+def test_plan_matches_gate_by_gate(n, tile_bits, run_bits, seed, dtype):
     glist = random_circuit_gates(n, 60, seed)
     st = R.random_state(n, "complex128", seed)
-    plan = planner.plan_queue(glist, n, MATS, tile_bits, run_bits, max_diag_bits=4 + seed % 3)
-    got = plan_interp.run_plan(st.copy(), plan, n, _raw(n))
+    plan = planner.plan_queue(glist, n, MATS, tile_bits, run_bits, max_diag_bits=4 + seed % 3, dtype=dtype)
+    got = plan_interp.run_plan(st.copy(), plan, n, _raw(n), nreg=planner.REG_BITS[dtype],
+                               fixed=(0,) if dtype == "complex64" else ())
     ref = R.reference_run(st, glist, n)
     np.testing.assert_allclose(got, ref, rtol=0, atol=1e-12)
 
@@ -39,12 +45,14 @@ def test_every_dense_target_is_local_and_passes_are_well_formed():
             continue
         local = seg[1]
         assert len(local) == 7 and local == sorted(set(local)) and local[:3] == [0, 1, 2]
-        for op in seg[2]:
-            assert len(set(op.targets) | set(op.controls)) == len(op.targets) + len(op.controls)
-            if op.kind == "dense":
-                assert set(op.targets) <= set(local) and len(op.targets) in (1, 2)
-            else:
-                assert len(op.targets) <= 10
+        for regs, ops in seg[2]:
+            assert len(regs) == 4 and set(regs) <= set(local)
+            for op in ops:
+                assert len(set(op.targets) | set(op.controls)) == len(op.targets) + len(op.controls)
+                if op.kind == "dense":
+                    assert set(op.targets) <= set(regs) and len(op.targets) in (1, 2)
+                else:
+                    assert len(op.targets) <= 10
 
 
 def test_qft_needs_few_passes_and_merges_its_phase_ladders():
@@ -52,8 +60,13 @@ def test_qft_needs_few_passes_and_merges_its_phase_ladders():
     plan = planner.plan_queue(circuits.qft(n).queue, n, MATS, 12, 5)
     assert all(seg[0] == "pass" for seg in plan)
     assert len(plan) <= 9                      # 577 gates, 577 passes gate by gate
-    nops = sum(len(seg[2]) for seg in plan)
-    assert nops < 577 // 3                     # 528 CU1 merged into far fewer tables
+    assert len(_ops(plan)) < 577 // 2          # 528 CU1 merged into far fewer tables
+    # a phase ladder's table touches at most two register bits of its round
+    for seg in plan:
+        for regs, ops in seg[2]:
+            for op in ops:
+                if op.kind == "diag":
+                    assert len(op.bits & set(regs)) <= 2
 
 
 def test_qft_plan_small_matches_analytic():
@@ -68,7 +81,17 @@ def test_qft_plan_small_matches_analytic():
 def test_diagonal_controls_are_split_off():
     n = 8
     glist = [gates.CU1(1, 0, 0.3), gates.CU1(2, 0, 0.5), gates.CU1(3, 0, 0.7)]
-    plan = planner.plan_queue(glist, n, MATS, 5, 3)
-    assert len(plan) == 1 and len(plan[0][2]) == 1
-    op = plan[0][2][0]
+    plan = planner.plan_queue(glist, n, MATS, 6, 3)
+    assert len(plan) == 1 and len(_ops(plan)) == 1
+    op = _ops(plan)[0]
     assert op.kind == "diag" and op.controls == (n - 1,) and len(op.targets) == 3
+
+
+def test_rounds_hoist_commuting_gates():
+    """Gates on disjoint qubits are packed into one round up to the register budget."""
+    n = 12
+    glist = [gates.H(q) for q in range(n)]
+    plan = planner.plan_queue(glist, n, MATS, 12, 5)
+    assert len(plan) == 1 and len(plan[0][2]) == 3      # 12 H gates, 4 register bits per round
+    plan64 = planner.plan_queue(glist, n, MATS, 12, 5, dtype="complex64")
+    assert len(plan64[0][2]) == 3 and all(0 in regs for regs, _ in plan64[0][2])

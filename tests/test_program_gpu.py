@@ -1,4 +1,4 @@
-"""-m gpu parity tests of the multi-gate pass kernel (`qj_program_*`, block_kernels.cu) against
+"""-m gpu parity tests of the multi-gate pass kernel (`qj_program_*`, pass_kernels.cu) against
 gate-by-gate application: the planner may only change the order of memory traffic."""
 
 import numpy as np
@@ -28,8 +28,9 @@ def _run(b, glist, st, n, dtype, **kw):
 
 @pytest.mark.parametrize("dtype", ["complex128", "complex64"])
 @pytest.mark.parametrize("seed", range(4))
-@pytest.mark.parametrize("n,tile_bits,run_bits", [(4, 4, 2), (6, 4, 2), (8, 5, 3), (9, 6, 1), (10, 10, 5),
-                                                  (7, 12, 5), (14, 12, 5), (16, 13, 6), (13, 11, 3)])
+@pytest.mark.parametrize("n,tile_bits,run_bits", [(4, 4, 2), (6, 6, 2), (8, 6, 3), (9, 7, 1), (10, 10, 5),
+                                                  (7, 12, 5), (14, 12, 5), (16, 13, 6), (13, 11, 3),
+                                                  (15, 12, 4), (12, 9, 6)])
 def test_program_matches_gate_by_gate(n, tile_bits, run_bits, seed, dtype):
     b = backend()
     glist = random_circuit_gates(n, 80, seed + 10 * n)
@@ -38,7 +39,7 @@ def test_program_matches_gate_by_gate(n, tile_bits, run_bits, seed, dtype):
                       max_diag_bits=4 + 2 * (seed % 4))
     ref = R.reference_run(st, glist, n)
     np.testing.assert_allclose(got, ref, rtol=0, atol=ATOL[dtype] * 20 if dtype == "complex64" else 1e-12)
-    assert stats["launches"] >= 1
+    assert stats["launches"] >= (1 if n >= planner.MIN_QUBITS else 0)
 
 
 @pytest.mark.parametrize("dtype", ["complex128", "complex64"])
@@ -88,23 +89,39 @@ def test_benchmark_circuits_program_vs_per_gate(workload):
     np.testing.assert_allclose(got, b.to_numpy(d), rtol=0, atol=1e-12)
 
 
-def test_program_rejects_nonlocal_dense_target():
+def _create(b, n, passes, rounds, ops, data):
     import ctypes
 
+    from qibojit_b200 import _capi
+
+    out = ctypes.c_void_p()
+    rc = b._lib.qj_program_create(b._handle(), _capi.QJ_C128, n, passes.ctypes.data, len(passes),
+                                  rounds.ctypes.data, len(rounds), ops.ctypes.data, len(ops),
+                                  data.ctypes.data, data.size, ctypes.byref(out))
+    return rc, out
+
+
+def test_program_rejects_dense_target_outside_the_registers():
     from qibojit_b200 import _capi
 
     b = backend()
     ops = np.zeros(1, dtype=planner.OP_DTYPE)
     ops[0]["kind"] = _capi.QJ_OPK_DENSE1
     ops[0]["ntargets"] = 1
-    ops[0]["targets"][0] = 9
+    rounds = np.zeros(1, dtype=planner.ROUND_DTYPE)
+    rounds[0]["nreg"] = 4
+    rounds[0]["nops"] = 1
+    rounds[0]["reg_bits"][:4] = [0, 1, 2, 3]
     passes = np.zeros(1, dtype=planner.PASS_DTYPE)
-    passes[0]["nlocal"] = 4
-    passes[0]["nops"] = 1
-    passes[0]["local_bits"][:4] = [0, 1, 2, 3]
+    passes[0]["nlocal"] = 6
+    passes[0]["nrounds"] = 1
+    passes[0]["local_bits"][:6] = [0, 1, 2, 3, 4, 5]
     data = np.eye(2, dtype=np.complex128).reshape(-1)
-    out = ctypes.c_void_p()
-    rc = b._lib.qj_program_create(b._handle(), _capi.QJ_C128, 10, passes.ctypes.data, 1,
-                                  ops.ctypes.data, 1, data.ctypes.data, 4, ctypes.byref(out))
-    assert rc == _capi.QJ_ERR_INVALID
-    assert b"not a local bit" in b._lib.qj_last_error()
+    for target, msg in [(9, b"not a local bit"), (5, b"not a register bit")]:
+        ops[0]["targets"][0] = target
+        rc, _ = _create(b, 10, passes, rounds, ops, data)
+        assert rc == _capi.QJ_ERR_INVALID
+        assert msg in b._lib.qj_last_error()
+    rounds[0]["reg_bits"][:4] = [0, 1, 2, 8]
+    rc, _ = _create(b, 10, passes, rounds, ops, data)
+    assert rc == _capi.QJ_ERR_INVALID and b"register bit is not a local bit" in b._lib.qj_last_error()

@@ -71,10 +71,11 @@ def main():
     print(f"{args.workload}-{n} {args.dtype} T={prog.tile_bits} r={prog.run_bits}: {len(c.queue)} gates -> "
           f"{stats['passes']} passes, {stats['launches']} launches, {stats['rounds']} rounds, "
           f"{stats['micro_ops']} micro-ops, {stats['raw_gates']} raw; plan+compile {t_plan*1e3:.0f} ms")
-    for (lb, ops), ms in zip(prog.passes, per):
+    for (lb, rounds), ms in zip(prog.passes, per):
+        ops = [o for _, ro in rounds for o in ro]
         nd = sum(1 for o in ops if o.kind == "diag")
-        print(f"  pass local={lb} ops={len(ops)} (dense {len(ops)-nd}, diag {nd}): {ms:8.3f} ms "
-              f"{full/ms/1e6:8.1f} GB/s")
+        print(f"  pass hi={lb[prog.run_bits:]} rounds={len(rounds)} ops={len(ops)} (dense {len(ops)-nd}, diag {nd}): "
+              f"{ms:8.3f} ms {full/ms/1e6:8.1f} GB/s")
     print(f"  total {total:.3f} ms -> {len(c.queue)/total*1e3:.1f} gates/s; norm={norm:.12f}")
     if args.out:
         with open(args.out, "a") as f:
