@@ -532,6 +532,27 @@ class B200Backend(_QiboBackend):
             return self.zero_state(nlocal, dtype=dtype)
         return torch.zeros(1 << nlocal, dtype=getattr(torch, str(dtype)), device=self.torch_device)
 
+    def shard_reset(self, shard, nlocal, one_at_zero=False):
+        if one_at_zero:
+            _capi.check(self._lib.qj_initial_state(self._handle(), shard.data_ptr(), self._tag(shard), nlocal))
+        else:
+            shard.zero_()
+        return shard
+
+    def run_local_segment(self, shard, nlocal, segment):
+        """Run the local gates between two exchanges: compiled once into multi-gate passes
+        (``planner.Program``, cached on the segment), or gate by gate when programs are off."""
+        if not getattr(self, "use_programs", True):
+            for gate in segment.gates:
+                shard = gate.apply(self, shard, nlocal)
+            return shard
+        if segment.compiled is None:
+            from ..planner import Program
+
+            segment.compiled = Program(self, segment.gates, nlocal,
+                                       dtype=str(shard.dtype).replace("torch.", ""))
+        return segment.compiled.run(shard)
+
     def shard_scale(self, shard, nlocal, phase):
         ph = np.asarray(phase, dtype=self._np_dtype(shard)).reshape(1)
         _capi.check(self._lib.qj_apply_phase(self._handle(), shard.data_ptr(), self._tag(shard),

@@ -66,11 +66,17 @@ enum {
     C_PERM1 = 16,     // + slot (X)
     C_DENSE2 = 24,    // + pair index (a < b): b (b - 1) / 2 + a
     C_PERM2 = 40,     // + pair index (SWAP)
-    C_DIAG1 = 56,     // one table look-up per thread, complex multiply of the masked elements
-    C_SIGN1 = 57,     // ... table of +-1: sign flip
-    C_DIAGC = 58,     // constant phase (payload)
-    C_SIGNC = 59,     // constant -1
+    C_DENSE1X = 50,   // + slot (real diagonal, imaginary off-diagonal: RX, Y, sqrt-X up to a phase)
+    C_PHASE = 56,     // product of per-thread table look-ups, one complex multiply of the selected elements
     C_DIAGN = 60,     // general: one look-up per element
+};
+
+// element selection of a C_PHASE op (which of a thread's register amplitudes the phase multiplies)
+enum {
+    SEL_ALL = 0,      // every element
+    SEL_SLOT = 1,     // + slot: elements whose register bit `slot` is 1
+    SEL_PAIR = 6,     // + pair index: elements whose register bits a and b are both 1
+    SEL_MASK = 16,    // arbitrary element mask
 };
 
 struct PassGeom {
@@ -129,62 +135,89 @@ __device__ __forceinline__ void load_units(const uint4 *p, float (&d)[4 * NU]) {
 }
 
 // ---- ops on the register amplitudes ---------------------------------------------------------------
-template <typename T, int A, bool REAL>
+// one-target gate on register slot A.  KIND 0: complex 2x2 (8 scalars), 1: real (4 scalars),
+// 2: real diagonal + imaginary off-diagonal, payload {g00, Im g01, Im g10, g11}.
+// The unmasked path (no register-slot controls) is straight-line code updating x in place.
+template <typename T, int A, int KIND>
+__device__ __forceinline__ void dense1_pair(Cx<T> &s0, Cx<T> &s1, const T *m) {
+    if (KIND == 1) {
+        const T t0 = m[1] * s1.re, t1 = m[1] * s1.im, u0 = m[2] * s0.re, u1 = m[2] * s0.im;
+        s0.re = fma(m[0], s0.re, t0); s0.im = fma(m[0], s0.im, t1);
+        s1.re = fma(m[3], s1.re, u0); s1.im = fma(m[3], s1.im, u1);
+    } else if (KIND == 2) {
+        const T t0 = m[1] * s1.im, t1 = m[1] * s1.re, u0 = m[2] * s0.im, u1 = m[2] * s0.re;
+        s0.re = fma(m[0], s0.re, -t0); s0.im = fma(m[0], s0.im, t1);
+        s1.re = fma(m[3], s1.re, -u0); s1.im = fma(m[3], s1.im, u1);
+    } else {
+        T ar = m[0] * s0.re, ai = m[0] * s0.im;
+        ar = fma(-m[1], s0.im, ar); ai = fma(m[1], s0.re, ai);
+        cmul_acc(ar, ai, m[2], m[3], s1.re, s1.im);
+        T br = m[4] * s0.re, bi = m[4] * s0.im;
+        br = fma(-m[5], s0.im, br); bi = fma(m[5], s0.re, bi);
+        cmul_acc(br, bi, m[6], m[7], s1.re, s1.im);
+        s0.re = ar; s0.im = ai; s1.re = br; s1.im = bi;
+    }
+}
+
+template <typename T, int A, int KIND>
 __device__ __forceinline__ void op_dense1(Cx<T> (&x)[Lay<T>::N], const uint4 *pay, uint32_t emask) {
     constexpr int N = Lay<T>::N;
     if constexpr (A < Lay<T>::J) {
-        constexpr int NS = REAL ? 4 : 8;                 // scalars in the payload (a whole number of units)
+        constexpr int NS = (KIND == 0) ? 8 : 4;          // scalars in the payload (a whole number of units)
         T m[NS];
         load_units<NS * sizeof(T) / 16>(pay, m);
+        if (emask == (N == 32 ? 0xffffffffu : 0xffffu)) {
 #pragma unroll
-        for (int p = 0; p < N / 2; p++) {
-            const int e0 = insert0(p, A), e1 = e0 | (1 << A);
-            if (!((emask >> e0) & 1u)) continue;
-            const Cx<T> s0 = x[e0], s1 = x[e1];
-            Cx<T> y0, y1;
-            if (REAL) {
-                y0.re = fma(m[0], s0.re, m[1] * s1.re);
-                y0.im = fma(m[0], s0.im, m[1] * s1.im);
-                y1.re = fma(m[2], s0.re, m[3] * s1.re);
-                y1.im = fma(m[2], s0.im, m[3] * s1.im);
-            } else {
-                y0.re = m[0] * s0.re; y0.im = m[0] * s0.im;
-                y0.re = fma(-m[1], s0.im, y0.re); y0.im = fma(m[1], s0.re, y0.im);
-                cmul_acc(y0.re, y0.im, m[2], m[3], s1.re, s1.im);
-                y1.re = m[4] * s0.re; y1.im = m[4] * s0.im;
-                y1.re = fma(-m[5], s0.im, y1.re); y1.im = fma(m[5], s0.re, y1.im);
-                cmul_acc(y1.re, y1.im, m[6], m[7], s1.re, s1.im);
+            for (int p = 0; p < N / 2; p++) {
+                const int e0 = insert0(p, A), e1 = e0 | (1 << A);
+                dense1_pair<T, A, KIND>(x[e0], x[e1], m);
             }
-            x[e0] = y0; x[e1] = y1;
+        } else {
+#pragma unroll
+            for (int p = 0; p < N / 2; p++) {
+                const int e0 = insert0(p, A), e1 = e0 | (1 << A);
+                if (!((emask >> e0) & 1u)) continue;
+                dense1_pair<T, A, KIND>(x[e0], x[e1], m);
+            }
         }
     }
 }
 
 // two-target gate: matrix-index bit 0 <-> slot A, bit 1 <-> slot B (A < B)
 template <typename T, int A, int B>
+__device__ __forceinline__ void dense2_group(Cx<T> (&x)[Lay<T>::N], const uint4 *pay, int e0) {
+    constexpr int RU = 8 * sizeof(T) / 16;           // units per matrix row (4 complex)
+    Cx<T> s[4], y[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) s[j] = x[e0 | ((j & 1) << A) | ((j >> 1) << B)];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        T g[8];
+        load_units<RU>(pay + i * RU, g);
+        T ar = g[0] * s[0].re, ai = g[0] * s[0].im;
+        ar = fma(-g[1], s[0].im, ar); ai = fma(g[1], s[0].re, ai);
+#pragma unroll
+        for (int j = 1; j < 4; j++) cmul_acc(ar, ai, g[2 * j], g[2 * j + 1], s[j].re, s[j].im);
+        y[i].re = ar; y[i].im = ai;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) x[e0 | ((i & 1) << A) | ((i >> 1) << B)] = y[i];
+}
+
+template <typename T, int A, int B>
 __device__ __forceinline__ void op_dense2(Cx<T> (&x)[Lay<T>::N], const uint4 *pay, uint32_t emask) {
     constexpr int N = Lay<T>::N;
     if constexpr (B < Lay<T>::J) {
-        constexpr int RU = 8 * sizeof(T) / 16;           // units per matrix row (4 complex)
+        if (emask == (N == 32 ? 0xffffffffu : 0xffffu)) {
 #pragma unroll
-        for (int p = 0; p < N / 4; p++) {
-            const int e0 = insert0(insert0(p, A), B);
-            if (!((emask >> e0) & 1u)) continue;
-            Cx<T> s[4], y[4];
+            for (int p = 0; p < N / 4; p++) dense2_group<T, A, B>(x, pay, insert0(insert0(p, A), B));
+        } else {
 #pragma unroll
-            for (int j = 0; j < 4; j++) s[j] = x[e0 | ((j & 1) << A) | ((j >> 1) << B)];
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                T g[8];
-                load_units<RU>(pay + i * RU, g);
-                T ar = g[0] * s[0].re, ai = g[0] * s[0].im;
-                ar = fma(-g[1], s[0].im, ar); ai = fma(g[1], s[0].re, ai);
-#pragma unroll
-                for (int j = 1; j < 4; j++) cmul_acc(ar, ai, g[2 * j], g[2 * j + 1], s[j].re, s[j].im);
-                y[i].re = ar; y[i].im = ai;
+            for (int p = 0; p < N / 4; p++) {
+                const int e0 = insert0(insert0(p, A), B);
+                if (!((emask >> e0) & 1u)) continue;
+                dense2_group<T, A, B>(x, pay, e0);
             }
-#pragma unroll
-            for (int i = 0; i < 4; i++) x[e0 | ((i & 1) << A) | ((i >> 1) << B)] = y[i];
         }
     }
 }
@@ -217,13 +250,18 @@ __device__ __forceinline__ void op_perm2(Cx<T> (&x)[Lay<T>::N], uint32_t emask) 
 }
 
 template <typename T>
+__device__ __forceinline__ void cmul_inplace(Cx<T> &v, T pr, T pi) {
+    const T t = pi * v.im, u = pi * v.re;
+    v.re = fma(pr, v.re, -t);
+    v.im = fma(pr, v.im, u);
+}
+
+template <typename T>
 __device__ __forceinline__ void mul_masked(Cx<T> (&x)[Lay<T>::N], uint32_t emask, T pr, T pi) {
 #pragma unroll
     for (int e = 0; e < Lay<T>::N; e++) {
         if (!((emask >> e) & 1u)) continue;
-        const Cx<T> v = x[e];
-        x[e].re = fma(pr, v.re, -pi * v.im);
-        x[e].im = fma(pr, v.im, pi * v.re);
+        cmul_inplace<T>(x[e], pr, pi);
     }
 }
 
@@ -239,6 +277,38 @@ __device__ __forceinline__ void flip_masked(Cx<T> (&x)[Lay<T>::N], uint32_t emas
         if (!((emask >> e) & 1u)) continue;
         x[e].re = flip(x[e].re, s);
         x[e].im = flip(x[e].im, s);
+    }
+}
+
+// phase (SIGN = false) or sign flip (SIGN = true) of the elements with every bit of the static
+// mask BITS set: straight-line code
+template <typename T, int BITS, bool SIGN>
+__device__ __forceinline__ void phase_static(Cx<T> (&x)[Lay<T>::N], T pr, T pi, uint32_t sg) {
+    if constexpr (BITS < Lay<T>::N) {
+#pragma unroll
+        for (int e = 0; e < Lay<T>::N; e++) {
+            if ((e & BITS) != BITS) continue;
+            if (SIGN) { x[e].re = flip(x[e].re, sg); x[e].im = flip(x[e].im, sg); }
+            else cmul_inplace<T>(x[e], pr, pi);
+        }
+    }
+}
+
+template <typename T, bool SIGN>
+__device__ __forceinline__ void phase_apply(Cx<T> (&x)[Lay<T>::N], uint32_t sel, uint32_t emask, T pr, T pi,
+                                            uint32_t sg) {
+    switch (sel) {
+#define QJ_PH(CODE, BITS) case CODE: phase_static<T, BITS, SIGN>(x, pr, pi, sg); break;
+        QJ_PH(SEL_ALL, 0)
+        QJ_PH(SEL_SLOT + 0, 1) QJ_PH(SEL_SLOT + 1, 2) QJ_PH(SEL_SLOT + 2, 4) QJ_PH(SEL_SLOT + 3, 8)
+        QJ_PH(SEL_SLOT + 4, 16)
+        QJ_PH(SEL_PAIR + 0, 3) QJ_PH(SEL_PAIR + 1, 5) QJ_PH(SEL_PAIR + 2, 6) QJ_PH(SEL_PAIR + 3, 9)
+        QJ_PH(SEL_PAIR + 4, 10) QJ_PH(SEL_PAIR + 5, 12) QJ_PH(SEL_PAIR + 6, 17) QJ_PH(SEL_PAIR + 7, 18)
+        QJ_PH(SEL_PAIR + 8, 20) QJ_PH(SEL_PAIR + 9, 24)
+#undef QJ_PH
+        default:
+            if (SIGN) flip_masked<T>(x, emask, sg);
+            else mul_masked<T>(x, emask, pr, pi);
     }
 }
 
@@ -392,54 +462,91 @@ k_pass(Cx<T> *__restrict__ state, const __grid_constant__ PassGeom pg, const uin
                     const uint4 h0 = op[0], h1 = op[1];
                     const uint4 *pay = op + 2;
                     op += h0.x >> 16;
-                    const uint32_t code = h0.x & 0xffffu, oslot = h0.y & 0xffffu, tmask = h0.z, emask = h0.w;
+                    const uint32_t code = h0.x & 0xffffu, emask = h0.w;
                     int oi = 0;
-                    if (oslot != 0xffffu) {
-                        oi = s_outer[oslot];
-                        if (oi < 0) continue;                       // outer control not satisfied by this tile
+                    if (code != C_PHASE) {  // (a phase group keeps the predicates per table)
+                        const uint32_t oslot = h0.y & 0xffffu, tmask = h0.z;
+                        if (oslot != 0xffffu) {
+                            oi = s_outer[oslot];
+                            if (oi < 0) continue;                   // outer control not satisfied by this tile
+                        }
+                        if ((base & tmask) != tmask) continue;      // tile-local control outside the registers
                     }
-                    if ((base & tmask) != tmask) continue;          // tile-local control outside the registers
                     switch (code) {
-#define QJ_D1C(A) op_dense1<T, A, false>(x, pay, emask)
-#define QJ_D1R(A) op_dense1<T, A, true>(x, pay, emask)
+#define QJ_D1C(A) op_dense1<T, A, 0>(x, pay, emask)
+#define QJ_D1R(A) op_dense1<T, A, 1>(x, pay, emask)
+#define QJ_D1X(A) op_dense1<T, A, 2>(x, pay, emask)
 #define QJ_P1(A) op_perm1<T, A>(x, emask)
 #define QJ_D2(A, B) op_dense2<T, A, B>(x, pay, emask)
 #define QJ_P2(A, B) op_perm2<T, A, B>(x, emask)
                         QJ_SLOT_CASES(C_DENSE1C, QJ_D1C)
                         QJ_SLOT_CASES(C_DENSE1R, QJ_D1R)
+                        QJ_SLOT_CASES(C_DENSE1X, QJ_D1X)
                         QJ_SLOT_CASES(C_PERM1, QJ_P1)
                         QJ_PAIR_CASES(C_DENSE2, QJ_D2)
                         QJ_PAIR_CASES(C_PERM2, QJ_P2)
 #undef QJ_D1C
 #undef QJ_D1R
+#undef QJ_D1X
 #undef QJ_P1
 #undef QJ_D2
 #undef QJ_P2
-                        case C_DIAGC: {
-                            T ph[16 / sizeof(T)];
-                            load_units<1>(pay, ph);
-                            mul_masked<T>(x, emask, ph[0], ph[1]);
-                        } break;
-                        case C_SIGNC:
-                            flip_masked<T>(x, emask, 0x80000000u);
-                            break;
-                        case C_DIAG1:
-                        case C_SIGN1: {
-                            const int nf = int(h0.y >> 16);
-                            int idx = oi;
-                            if (nf > 0) idx |= field_of(base, h1.y);
-                            if (nf > 1) idx |= field_of(base, h1.z);
-                            if (nf > 2) idx |= field_of(base, h1.w);
-                            if (nf > 3) {
-                                const uint4 f = pay[0];
-                                idx |= field_of(base, f.x);
-                                if (nf > 4) idx |= field_of(base, f.y);
-                                if (nf > 5) idx |= field_of(base, f.z);
-                                if (nf > 6) idx |= field_of(base, f.w);
+                        case C_PHASE: {
+                            // h0.y = ntab | sel << 16, h0.z = all-sign flag; descriptors: 2 (<= 5 fields)
+                            // or 3 units: {table, nf | oslot << 16, tmask, f0} {f1..f4} {f5..f8}
+                            const int ntab = int(h0.y & 0xffffu);
+                            const uint32_t sel = h0.y >> 16;
+                            const bool allsign = h0.z != 0u;
+                            const uint4 *d = pay;
+                            Cx<T> ph;
+                            ph.re = T(1); ph.im = T(0);
+                            uint32_t sg = 0;
+                            bool any = false;
+#pragma unroll 1
+                            for (int t = 0; t < ntab; t++) {
+                                const uint4 d0 = d[0], d1 = d[1];
+                                const int nf = int(d0.y & 0xffffu);
+                                const uint32_t osl = d0.y >> 16;
+                                const uint4 *const dx = d + 2;
+                                d += (nf > 5) ? 3 : 2;
+                                int idx = 0;
+                                if (osl != 0xffffu) {
+                                    idx = s_outer[osl];
+                                    if (idx < 0) continue;                   // outer control not satisfied
+                                }
+                                if ((base & d0.z) != d0.z) continue;         // tile-local control outside the registers
+                                if (nf > 0) idx |= field_of(base, d0.w);
+                                if (nf > 1) {
+                                    idx |= field_of(base, d1.x);
+                                    if (nf > 2) idx |= field_of(base, d1.y);
+                                    if (nf > 3) idx |= field_of(base, d1.z);
+                                    if (nf > 4) idx |= field_of(base, d1.w);
+                                    if (nf > 5) {
+                                        const uint4 d2 = dx[0];
+                                        idx |= field_of(base, d2.x);
+                                        if (nf > 6) idx |= field_of(base, d2.y);
+                                        if (nf > 7) idx |= field_of(base, d2.z);
+                                        if (nf > 8) idx |= field_of(base, d2.w);
+                                    }
+                                }
+                                const Cx<T> z = ldg_cx(tables + d0.x + idx);
+                                if (allsign) {
+                                    sg ^= sign_of(z.re);
+                                } else if (!any) {
+                                    ph = z;
+                                } else {
+                                    const T nr = fma(ph.re, z.re, -(ph.im * z.im));
+                                    ph.im = fma(ph.re, z.im, ph.im * z.re);
+                                    ph.re = nr;
+                                }
+                                any = true;
                             }
-                            const Cx<T> ph = ldg_cx(tables + h1.x + idx);
-                            if (code == C_SIGN1) flip_masked<T>(x, emask, sign_of(ph.re));
-                            else mul_masked<T>(x, emask, ph.re, ph.im);
+                            if (!any) break;
+                            if (allsign) {
+                                if (sg) phase_apply<T, true>(x, sel, emask, T(0), T(0), sg);
+                            } else {
+                                phase_apply<T, false>(x, sel, emask, ph.re, ph.im, 0u);
+                            }
                         } break;
                         default: {  // C_DIAGN: table index = outer part | fields of the base | element part
                             const int nf = int(h0.y >> 16);
@@ -767,6 +874,69 @@ extern "C" int qj_program_create(qj_handle *h, int dtype, int nqubits, const qj_
                 r_nops++;
             };
 
+            // diagonal slices wait here and are emitted as phase groups: the slices of a run of
+            // consecutive diagonal ops commute, so those that multiply the same elements are merged
+            // into ONE op (thread-level product of the look-ups, one multiply per element)
+            struct PendingSlice {
+                uint32_t emask, tmask, table;
+                int oslot, nf;
+                uint32_t fields[9];
+                bool sign;
+            };
+            std::vector<PendingSlice> pending;
+            auto select_code = [&](uint32_t emask) -> uint32_t {
+                const uint32_t full = (N == 32) ? 0xffffffffu : 0xffffu;
+                if (emask == full) return SEL_ALL;
+                for (int a = 0; a < J; a++) {
+                    uint32_t m = 0;
+                    for (int e = 0; e < N; e++) if ((e >> a) & 1) m |= 1u << e;
+                    if (m == emask) return SEL_SLOT + uint32_t(a);
+                }
+                for (int b2 = 1; b2 < J; b2++)
+                    for (int a = 0; a < b2; a++) {
+                        uint32_t m = 0;
+                        for (int e = 0; e < N; e++) if (((e >> a) & 1) && ((e >> b2) & 1)) m |= 1u << e;
+                        if (m == emask) return SEL_PAIR + uint32_t(pair_index(a, b2));
+                    }
+                return SEL_MASK;
+            };
+            auto flush_pending = [&]() {
+                std::vector<bool> done(pending.size(), false);
+                for (size_t i = 0; i < pending.size(); i++) {
+                    if (done[i]) continue;
+                    std::vector<Unit> payload;
+                    int ntab = 0;
+                    bool allsign = true;
+                    for (size_t j = i; j < pending.size(); j++)
+                        if (!done[j] && pending[j].emask == pending[i].emask) allsign = allsign && pending[j].sign;
+                    for (size_t j = i; j < pending.size(); j++) {
+                        if (done[j] || pending[j].emask != pending[i].emask) continue;
+                        done[j] = true;
+                        const PendingSlice &ps = pending[j];
+                        Unit d0, d1, d2;
+                        memset(&d1, 0, sizeof(d1)); memset(&d2, 0, sizeof(d2));
+                        d0.w[0] = ps.table;
+                        d0.w[1] = uint32_t(ps.nf) | (uint32_t(ps.oslot) << 16);
+                        d0.w[2] = ps.tmask;
+                        d0.w[3] = ps.fields[0];
+                        for (int f = 0; f < 4; f++) { d1.w[f] = ps.fields[1 + f]; d2.w[f] = ps.fields[5 + f]; }
+                        payload.push_back(d0); payload.push_back(d1);
+                        if (ps.nf > 5) payload.push_back(d2);
+                        ntab++;
+                    }
+                    Unit h0, h1;
+                    memset(&h1, 0, sizeof(h1));
+                    h0.w[0] = uint32_t(C_PHASE) | (uint32_t(2 + payload.size()) << 16);
+                    h0.w[1] = uint32_t(ntab) | (select_code(pending[i].emask) << 16);
+                    h0.w[2] = allsign ? 1u : 0u;
+                    h0.w[3] = pending[i].emask;
+                    r_ops.push_back(h0); r_ops.push_back(h1);
+                    r_ops.insert(r_ops.end(), payload.begin(), payload.end());
+                    r_nops++;
+                }
+                pending.clear();
+            };
+
             for (int64_t oi = rdesc.first_op; oi < rdesc.first_op + rdesc.nops; oi++) {
                 const qj_op_desc &od = ops[oi];
                 if (od.ncontrols < 0 || od.ncontrols > QJ_MAX_QUBITS) return bail("op: bad control count");
@@ -787,6 +957,7 @@ extern "C" int qj_program_create(qj_handle *h, int dtype, int nqubits, const qj_
                 for (int e = 0; e < N; e++) if ((elem_bits(e) & rcmask) == rcmask) cmask_e |= 1u << e;
 
                 if (od.kind == QJ_OPK_DENSE1 || od.kind == QJ_OPK_DENSE2) {
+                    flush_pending();
                     const int nt = (od.kind == QJ_OPK_DENSE1) ? 1 : 2;
                     if (od.ntargets != nt) return bail("op: dense target count mismatch");
                     const int64_t need = (nt == 1) ? 4 : 16;
@@ -814,6 +985,9 @@ extern "C" int qj_program_create(qj_handle *h, int dtype, int nqubits, const qj_
                         } else if (real) {
                             enc.push_scalars(payload, {m[0].real(), m[1].real(), m[2].real(), m[3].real()});
                             push_op(C_DENSE1R + sl[0], oslot, 0, tmask, cmask_e, 0, nullptr, payload);
+                        } else if (m[0].imag() == 0.0 && m[3].imag() == 0.0 && m[1].real() == 0.0 && m[2].real() == 0.0) {
+                            enc.push_scalars(payload, {m[0].real(), m[1].imag(), m[2].imag(), m[3].real()});
+                            push_op(C_DENSE1X + sl[0], oslot, 0, tmask, cmask_e, 0, nullptr, payload);
                         } else {
                             std::vector<double> s;
                             for (const cd &z : m) { s.push_back(z.real()); s.push_back(z.imag()); }
@@ -864,7 +1038,7 @@ extern "C" int qj_program_create(qj_handle *h, int dtype, int nqubits, const qj_
                     const int nthr = int(thr.size()), nout = int(outb.size()), k = int(regj.size());
                     if (nout > 11) return bail("op: diagonal table over more than 11 bits outside the tile");
                     // thread fields: runs of consecutive local positions
-                    uint32_t fields[8] = {0};
+                    uint32_t fields[10] = {0};
                     int nf = 0;
                     for (int i = 0; i < nthr; i++) {
                         if (nf > 0) {
@@ -872,7 +1046,7 @@ extern "C" int qj_program_create(qj_handle *h, int dtype, int nqubits, const qj_
                             const int src = fl & 255, len = (fl >> 8) & 255;
                             if (src + len == thr[i].first) { fields[nf - 1] = fl + (1u << 8); continue; }
                         }
-                        if (nf == 7) return bail("op: diagonal table needs too many bit fields");
+                        if (nf == 9) return bail("op: diagonal table needs too many bit fields");
                         fields[nf++] = uint32_t(thr[i].first) | (1u << 8) | (uint32_t(i) << 16);
                     }
                     for (int i = 0; i < nout; i++) {
@@ -917,25 +1091,19 @@ extern "C" int qj_program_create(qj_handle *h, int dtype, int nqubits, const qj_
                                 for (int i = 0; i < k && ok; i++) ok = ((e >> regslot[i]) & 1) == ((sl.a >> i) & 1);
                                 if (ok) emask |= 1u << e;
                             }
-                            payload.clear();
-                            if (nsub == 0) {
-                                if (sl.sign) {
-                                    push_op(C_SIGNC, oslot, 0, tmask, emask, 0, nullptr, payload);
-                                } else {
-                                    enc.push_scalars(payload, {sl.t[0].real(), sl.t[0].imag()});
-                                    push_op(C_DIAGC, oslot, 0, tmask, emask, 0, nullptr, payload);
-                                }
-                                continue;
-                            }
-                            if (nf > 3) {
-                                Unit u;
-                                for (int i = 0; i < 4; i++) u.w[i] = fields[3 + i];
-                                payload.push_back(u);
-                            }
-                            push_op(sl.sign ? C_SIGN1 : C_DIAG1, oslot, nf, tmask, emask, enc.push_table(sl.t), fields, payload);
+                            if (emask == 0) continue;
+                            PendingSlice ps;
+                            memset(&ps, 0, sizeof(ps));
+                            ps.emask = emask; ps.tmask = tmask; ps.oslot = oslot; ps.nf = nf;
+                            for (int f = 0; f < nf; f++) ps.fields[f] = fields[f];
+                            ps.sign = sl.sign;
+                            ps.table = enc.push_table(sl.t);   // a constant phase is a one-entry table
+                            pending.push_back(ps);
                         }
                     } else {
                         // general table: index = thread fields | outer bits | register bits
+                        flush_pending();
+                        if (nf > 7) return bail("op: diagonal table needs too many bit fields");
                         std::vector<cd> t(size_t(1) << nb);
                         for (int a = 0; a < (1 << k); a++)
                             for (int s = 0; s < (1 << nsub); s++)
@@ -954,6 +1122,8 @@ extern "C" int qj_program_create(qj_handle *h, int dtype, int nqubits, const qj_
                 }
             }
 
+            flush_pending();
+
             // append the round (closing the launch first when the image would overflow)
             const size_t need_units = 1 + round_units.size() + 3 + outer_units.size() + r_outer.size() + op_units.size() + r_ops.size();
             if (3 + r_outer.size() + r_ops.size() + 1 > size_t(kMaxBlobUnits) || r_outer.size() / 2 > size_t(kMaxOuter))
@@ -963,8 +1133,18 @@ extern "C" int qj_program_create(qj_handle *h, int dtype, int nqubits, const qj_
                 close_launch();
                 for (size_t i = 0; i < r_ops.size();) {
                     const uint32_t units = r_ops[i].w[0] >> 16;
-                    const uint32_t oslot = r_ops[i].w[1] & 0xffffu;
-                    if (oslot != 0xffffu) r_ops[i].w[1] = (r_ops[i].w[1] & 0xffff0000u) | (oslot - uint32_t(outer_base));
+                    if ((r_ops[i].w[0] & 0xffffu) == uint32_t(C_PHASE)) {  // slots live in the table descriptors
+                        const int ntab = int(r_ops[i].w[1] & 0xffffu);
+                        size_t d = i + 2;
+                        for (int t = 0; t < ntab; t++) {
+                            const uint32_t nf = r_ops[d].w[1] & 0xffffu, oslot = r_ops[d].w[1] >> 16;
+                            if (oslot != 0xffffu) r_ops[d].w[1] = nf | ((oslot - uint32_t(outer_base)) << 16);
+                            d += (nf > 5) ? 3 : 2;
+                        }
+                    } else {
+                        const uint32_t oslot = r_ops[i].w[1] & 0xffffu;
+                        if (oslot != 0xffffu) r_ops[i].w[1] = (r_ops[i].w[1] & 0xffff0000u) | (oslot - uint32_t(outer_base));
+                    }
                     i += units;
                 }
             }

@@ -79,6 +79,62 @@ def is_diagonal_matrix(m, tol=0.0):
     return bool(np.all(np.abs(off) <= tol))
 
 
+class LocalGate:
+    """One rank's share of a gate, in the numbering of its nlocal-qubit shard register: global
+    controls resolved by the rank predicate, global diagonal targets fixed to the rank's bit
+    values.  Duck-types the gate attributes ``planner.lower_gate`` and the per-gate dispatch read."""
+
+    diagonal = False
+
+    def __init__(self, op, targets, controls, kernel_matrix, dense):
+        self.op = op                          # reference kernel name (GATE_OPS value) or None
+        self.target_qubits = tuple(int(t) for t in targets)
+        self.control_qubits = tuple(int(c) for c in controls)
+        self.kernel_matrix = kernel_matrix    # what the reference-style kernel entry consumes
+        self.dense = np.asarray(dense)        # 2^t x 2^t target-only matrix
+        self.name = "localgate"
+        self.parameters = ()
+
+    @property
+    def qubits(self):
+        return self.control_qubits + self.target_qubits
+
+    def target_matrix(self, matrices):
+        return self.dense.astype(matrices.dtype)
+
+    def apply(self, backend, state, nqubits):
+        """Gate-by-gate execution through the reference-style kernel entry points."""
+        t = self.target_qubits
+        bits = sorted(nqubits - 1 - q for q in self.qubits)
+        qubits = np.array(bits, dtype=np.int32) if self.control_qubits else None
+        if self.op is None:
+            matrix = self.target_matrix(backend.custom_matrices)
+        else:
+            matrix = self.kernel_matrix
+        if len(t) == 1:
+            return backend._one_qubit_base(state, nqubits, t[0], self.op or "apply_gate", matrix, qubits)
+        if len(t) == 2:
+            return backend._two_qubit_base(state, nqubits, t[0], t[1], self.op or "apply_two_qubit_gate",
+                                           matrix, qubits)
+        return backend._multi_qubit_base(state, nqubits, list(t), matrix, np.array(bits, dtype=np.int32))
+
+
+class LocalSegment:
+    """A run of local gates between two exchanges; `compiled` caches the backend's program."""
+
+    def __init__(self):
+        self.gates = []
+        self.compiled = None
+
+
+class Exchange:
+    """Swap rank bit `rank_bit` with shard index bit `local_bit` (half a shard each way)."""
+
+    def __init__(self, rank_bit, local_bit):
+        self.rank_bit = int(rank_bit)
+        self.local_bit = int(local_bit)
+
+
 class DistributedState:
     """A 2^nqubits state vector sharded over the ranks of `comm`."""
 
@@ -95,8 +151,8 @@ class DistributedState:
         # logical qubit -> physical index bit; bits >= nlocal are the rank bits
         self.bit_of = [self.nqubits - 1 - q for q in range(self.nqubits)]
         self.swap_chunk_bytes = swap_chunk_bytes
-        self.stats = {"exchanges": 0, "exchange_bytes": 0, "local_passes": 0, "skipped": 0,
-                      "relabelled_swaps": 0}
+        self.stats = {"exchanges": 0, "exchange_bytes": 0, "local_gates": 0, "local_segments": 0,
+                      "skipped": 0, "relabelled_swaps": 0}
         self.shard = backend.shard_zeros(self.nlocal, self.dtype, one_at_zero=(self.rank == 0))
 
     # ------------------------------------------------------------------ helpers
@@ -117,16 +173,9 @@ class DistributedState:
     # ------------------------------------------------------------------ exchange
     def swap_global_local(self, qglobal, qlocal):
         """Exchange the roles of a global and a local qubit (ops.swap_pieces semantics)."""
-        gbit, lbit = self.bit_of[qglobal], self.bit_of[qlocal]
-        assert gbit >= self.nlocal > lbit
-        j = gbit - self.nlocal
-        peer = self.rank ^ (1 << j)
-        is_upper = (self.rank >> j) & 1
-        moved = self.backend.shard_exchange(self.shard, self.nlocal, lbit, peer, is_upper, self.comm,
-                                            self.swap_chunk_bytes)
-        self.bit_of[qglobal], self.bit_of[qlocal] = lbit, gbit
-        self.stats["exchanges"] += 1
-        self.stats["exchange_bytes"] += int(moved)
+        steps = []
+        self._plan_exchange(steps, qglobal, qlocal)
+        return self.run(steps)
 
     def _choose_victim(self, protected, lookahead):
         """Local qubit whose next use as a non-diagonal target lies farthest in the future."""
@@ -150,15 +199,28 @@ class DistributedState:
                 victim = self._choose_victim(set(qubits), lookahead)
                 self.swap_global_local(q, victim)
 
-    # ------------------------------------------------------------------ gate application
-    def apply_gate(self, gate, lookahead=None):
-        b = self.backend
+    # ------------------------------------------------------------------ planning
+    def _emit(self, plan, gate):
+        if not plan or not isinstance(plan[-1], LocalSegment):
+            plan.append(LocalSegment())
+        plan[-1].gates.append(gate)
+        self.stats["local_gates"] += 1
+
+    def _plan_exchange(self, plan, qglobal, qlocal):
+        gbit, lbit = self.bit_of[qglobal], self.bit_of[qlocal]
+        assert gbit >= self.nlocal > lbit
+        plan.append(Exchange(gbit - self.nlocal, lbit))
+        self.bit_of[qglobal], self.bit_of[qlocal] = lbit, gbit
+
+    def _plan_gate(self, plan, gate, lookahead):
+        """Symbolic application of one gate: updates the qubit map and appends this rank's local
+        gate (shard numbering) and/or exchange steps to `plan`.  No amplitude is touched."""
         name = gate.__class__.__name__
         if getattr(gate, "name", "") == "fanout":
             from . import gates as G
 
             for t in gate.target_qubits:
-                self.apply_gate(G.CNOT(gate.control_qubits[0], t), lookahead)
+                self._plan_gate(plan, G.CNOT(gate.control_qubits[0], t), lookahead)
             return
         targets = list(gate.target_qubits)
         controls = list(gate.control_qubits)
@@ -171,7 +233,7 @@ class DistributedState:
             self.stats["relabelled_swaps"] += 1
             return
 
-        matrix = b._as_custom_matrix(gate)
+        matrix = self.backend._as_custom_matrix(gate)
 
         if op in _SYMMETRIC_PHASE_OPS:
             # phase on |1..1> of controls+target: symmetric in its qubits
@@ -181,79 +243,107 @@ class DistributedState:
                 return
             local = [q for q in qs if self.is_local(q)]
             phase = -1.0 if op == "apply_z" else complex(np.asarray(matrix).ravel()[0])
-            if not local:
-                b.shard_scale(self.shard, self.nlocal, phase)
-            else:
-                bits = sorted(self.bit_of[q] for q in local)
-                tbit = bits[0]
-                b._one_qubit_base(self.shard, self.nlocal, self._pseudo(tbit), op, matrix,
-                                  np.array(bits, dtype=np.int32) if len(bits) > 1 else None)
-            self.stats["local_passes"] += 1
+            self._emit_phase(plan, phase, local)
             return
 
-        # global controls: rank predicate
-        for q in controls:
-            if not self.is_local(q) and self.rank_bit(q) == 0:
-                self.stats["skipped"] += 1
-                return
+        # global controls: rank predicate.  An inactive rank still takes part in the exchanges a
+        # non-diagonal global target needs (its peers run the gate and every rank keeps one map).
+        active = all(self.is_local(q) or self.rank_bit(q) == 1 for q in controls)
         lcontrols = [q for q in controls if self.is_local(q)]
 
-        gtargets = [q for q in targets if not self.is_local(q)]
-        if gtargets:
+        dense = None
+        if any(not self.is_local(q) for q in targets):
             dense = self._dense_matrix(gate, matrix)
             if is_diagonal_matrix(dense):
-                self._apply_restricted_diagonal(np.diagonal(dense), targets, lcontrols)
-                return
-            self.ensure_local(targets, lookahead)
-            # a victim may have been one of this gate's local controls: re-evaluate them
-            for q in controls:
-                if not self.is_local(q) and self.rank_bit(q) == 0:
+                if active:
+                    self._emit_restricted_diagonal(plan, np.diagonal(dense), targets, lcontrols)
+                else:
                     self.stats["skipped"] += 1
-                    return
+                return
+            for q in targets:
+                if not self.is_local(q):
+                    victim = self._choose_victim(set(targets), lookahead or {})
+                    self._plan_exchange(plan, q, victim)
+            # a victim may have been one of this gate's local controls: re-evaluate them
+            active = all(self.is_local(q) or self.rank_bit(q) == 1 for q in controls)
             lcontrols = [q for q in controls if self.is_local(q)]
-
-        self._apply_local(op, name, matrix, targets, lcontrols)
+        if not active:
+            self.stats["skipped"] += 1
+            return
+        self._emit(plan, LocalGate(op, [self._pseudo(self.bit_of[q]) for q in targets],
+                                   [self._pseudo(self.bit_of[q]) for q in lcontrols], matrix,
+                                   dense if dense is not None else self._dense_matrix(gate, matrix)))
 
     def _dense_matrix(self, gate, matrix):
         from . import fusion
 
         return fusion.target_only_matrix(gate, self.backend.custom_matrices)
 
-    def _apply_local(self, op, name, matrix, targets, lcontrols):
-        b = self.backend
-        n = self.nlocal
-        tb = [self.bit_of[q] for q in targets]
-        bits = sorted(tb + [self.bit_of[q] for q in lcontrols])
-        qubits = np.array(bits, dtype=np.int32) if lcontrols else None
-        pt = [self._pseudo(x) for x in tb]
-        if len(targets) == 1:
-            b._one_qubit_base(self.shard, n, pt[0], op or "apply_gate", matrix, qubits)
-        elif len(targets) == 2:
-            b._two_qubit_base(self.shard, n, pt[0], pt[1], op or "apply_two_qubit_gate", matrix, qubits)
-        else:
-            b._multi_qubit_base(self.shard, n, pt, matrix, np.array(bits, dtype=np.int32))
-        self.stats["local_passes"] += 1
+    def _emit_phase(self, plan, phase, local):
+        """exp-phase on |1..1> of the local qubits `local` (all of the shard when empty)."""
+        if local:
+            ps = [self._pseudo(self.bit_of[q]) for q in local]
+            op = "apply_z" if phase == -1.0 else "apply_z_pow"
+            self._emit(plan, LocalGate(op, ps[-1:], ps[:-1], np.asarray(phase),
+                                       np.diag([1.0, complex(phase)])))
+        else:  # scalar phase of the whole shard: a diagonal gate that costs nothing inside a pass
+            self._emit(plan, LocalGate(None, [0], [], np.diag([complex(phase)] * 2),
+                                       np.diag([complex(phase)] * 2)))
 
-    def _apply_restricted_diagonal(self, diag, targets, lcontrols):
+    def _emit_restricted_diagonal(self, plan, diag, targets, lcontrols):
         """Diagonal gate with some targets global: fix those bits to the rank's values."""
-        b = self.backend
         t = len(targets)
         d = np.asarray(diag).reshape((2,) * t)
         index = tuple(self.rank_bit(q) if not self.is_local(q) else slice(None) for q in targets)
-        d = d[index]
+        d = np.asarray(d[index]).reshape(-1)
         ltargets = [q for q in targets if self.is_local(q)]
+        pc = [self._pseudo(self.bit_of[q]) for q in lcontrols]
         if ltargets:
-            d = np.asarray(d).reshape(-1)
-            self._apply_local(None, "Unitary", np.diag(d), ltargets, lcontrols)
-            return
-        phase = complex(d)
-        if not lcontrols:
-            b.shard_scale(self.shard, self.nlocal, phase)
+            m = np.diag(d)
+            self._emit(plan, LocalGate(None, [self._pseudo(self.bit_of[q]) for q in ltargets], pc, m, m))
+        elif not lcontrols:
+            self._emit_phase(plan, complex(d[0]), [])
         else:
-            bits = sorted(self.bit_of[q] for q in lcontrols)
-            b._one_qubit_base(self.shard, self.nlocal, self._pseudo(bits[0]), "apply_z_pow",
-                              np.asarray(phase), np.array(bits, dtype=np.int32) if len(bits) > 1 else None)
-        self.stats["local_passes"] += 1
+            self._emit_phase(plan, complex(d[0]), lcontrols)
+
+    def plan(self, queue):
+        """Gate list -> [LocalSegment | Exchange] for this rank, advancing the qubit map.  The
+        exchange steps are identical on every rank (victims depend on the map and on a look-ahead
+        over the list only); the local gates differ by the rank predicates."""
+        needs = [self._needs_local(g, self.backend.custom_matrices) for g in queue]
+        # table[i][q] = index of the next gate after i that needs q local
+        nxt = {}
+        table = [None] * len(queue)
+        for i in range(len(queue) - 1, -1, -1):
+            table[i] = dict(nxt)
+            for q in needs[i]:
+                nxt[q] = i
+        steps = []
+        for i, gate in enumerate(queue):
+            look = {q: (j - i) for q, j in table[i].items()}
+            self._plan_gate(steps, gate, look)
+        return steps
+
+    def run(self, steps):
+        """Execute planned steps on the shard (local segments are compiled into multi-gate pass
+        programs by the backend the first time they run, and cached on the step)."""
+        b = self.backend
+        for step in steps:
+            if isinstance(step, LocalSegment):
+                self.shard = b.run_local_segment(self.shard, self.nlocal, step)
+                self.stats["local_segments"] += 1
+            else:
+                peer = self.rank ^ (1 << step.rank_bit)
+                moved = b.shard_exchange(self.shard, self.nlocal, step.local_bit, peer,
+                                         (self.rank >> step.rank_bit) & 1, self.comm, self.swap_chunk_bytes)
+                self.stats["exchanges"] += 1
+                self.stats["exchange_bytes"] += int(moved)
+        return self
+
+    def apply_gate(self, gate, lookahead=None):
+        steps = []
+        self._plan_gate(steps, gate, lookahead)
+        return self.run(steps)
 
     # ------------------------------------------------------------------ circuits
     @staticmethod
@@ -273,18 +363,13 @@ class DistributedState:
         return list(gate.target_qubits)
 
     def execute(self, queue):
-        """Apply a gate list; swap victims are chosen with a look-ahead over the list."""
-        needs = [self._needs_local(g, self.backend.custom_matrices) for g in queue]
-        # next_use[i][q] = distance from gate i to q's next appearance in `needs`
-        nxt = {}
-        table = [None] * len(queue)
-        for i in range(len(queue) - 1, -1, -1):
-            table[i] = dict(nxt)
-            for q in needs[i]:
-                nxt[q] = i
-        for i, gate in enumerate(queue):
-            look = {q: (j - i) for q, j in table[i].items()}
-            self.apply_gate(gate, look)
+        """Apply a gate list: plan it (swap victims by look-ahead), then run the steps."""
+        return self.run(self.plan(queue))
+
+    def reset(self):
+        """Back to |0...0> with the identity qubit map (in place)."""
+        self.backend.shard_reset(self.shard, self.nlocal, one_at_zero=(self.rank == 0))
+        self.bit_of = [self.nqubits - 1 - q for q in range(self.nqubits)]
         return self
 
     # ------------------------------------------------------------------ results
@@ -323,5 +408,14 @@ def execute_distributed_circuit(backend, circuit, initial_state=None, nshots=Non
     if initial_state is not None:
         raise TypeError("distributed execution starts from |0...0>; initial states are not supported")
     state = DistributedState(backend, circuit.nqubits, comm=comm)
-    state.execute(circuit.queue)
+    key = ("dist", state.rank, state.comm.world, backend.dtype)
+    cache = circuit.__dict__.setdefault("_qj_programs", {})
+    if key in cache:
+        steps, final_map = cache[key]
+        state.run(steps)
+        state.bit_of = list(final_map)
+    else:
+        steps = state.plan(circuit.queue)
+        state.run(steps)
+        cache[key] = (steps, list(state.bit_of))
     return state

@@ -322,6 +322,7 @@ class Program:
         self.ngates = len(queue)
         self.segments = []       # ('program', handle, npasses) | ('raw', gate)
         self.passes = []         # [(local_bits, [(reg_bits, [PlanOp])])] for inspection
+        self.upload_bytes = 0    # host bytes handed to qj_program_create (descriptors + matrices/tables)
         if self.nqubits < MIN_QUBITS:   # too small for a tile: gate by gate
             self.segments = [("raw", g) for g in queue]
             return
@@ -380,6 +381,7 @@ class Program:
             b._handle(), _capi.QJ_C128 if self.dtype == "complex128" else _capi.QJ_C64, self.nqubits,
             pass_arr.ctypes.data, len(passes), round_arr.ctypes.data, nrounds, op_arr.ctypes.data, nops,
             data.ctypes.data, int(data.size), ctypes.byref(handle)))
+        self.upload_bytes += pass_arr.nbytes + round_arr.nbytes + op_arr.nbytes + data.nbytes
         self.segments.append(("program", handle, len(passes)))
         self.passes.extend(passes)
 

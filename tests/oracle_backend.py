@@ -11,8 +11,9 @@ from tests import refdispatch as R
 
 
 class OracleBackend:
-    def __init__(self, dtype="complex128"):
+    def __init__(self, dtype="complex128", via_planner=False):
         self.dtype = dtype
+        self.via_planner = via_planner   # lower local segments through planner.plan_queue
         self.custom_matrices = CustomMatrices(dtype)
         self.engine = torch
 
@@ -57,6 +58,26 @@ class OracleBackend:
         if one_at_zero:
             return self.zero_state(nlocal, dtype)
         return torch.zeros(1 << nlocal, dtype=getattr(torch, str(dtype)))
+
+    def shard_reset(self, shard, nlocal, one_at_zero=False):
+        shard.zero_()
+        if one_at_zero:
+            shard[0] = 1
+        return shard
+
+    def run_local_segment(self, shard, nlocal, segment):
+        if self.via_planner and nlocal >= 6:
+            from qibojit_b200 import planner
+            from tests import plan_interp
+
+            plan = planner.plan_queue(segment.gates, nlocal, self.custom_matrices, 6, 3, dtype=self.dtype)
+            st = plan_interp.run_plan(shard.numpy().astype(np.complex128), plan, nlocal,
+                                      lambda st, g: g.apply(self, torch.from_numpy(st), nlocal).numpy())
+            shard.copy_(torch.from_numpy(st.astype(self.dtype)))
+            return shard
+        for gate in segment.gates:
+            shard = gate.apply(self, shard, nlocal)
+        return shard
 
     def shard_scale(self, shard, nlocal, phase):
         shard.mul_(complex(phase))

@@ -53,7 +53,7 @@ def _test_circuits(n):
             "qv": circuits.quantum_volume(n, depth=3), "mixed": mixed, "mixed_fused": mixed.fuse(3)}
 
 
-def _worker(rank, world, port, n, dtype, q):
+def _worker(rank, world, port, n, dtype, q, via_planner=False):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -64,7 +64,7 @@ def _worker(rank, world, port, n, dtype, q):
 
         results = {}
         for name, circuit in _test_circuits(n).items():
-            b = OracleBackend(dtype)
+            b = OracleBackend(dtype, via_planner=via_planner)
             ds = DistributedState(b, n, comm=Comm(), dtype=dtype)
             ds.execute(circuit.queue)
             full = ds.to_numpy_full()
@@ -76,13 +76,15 @@ def _worker(rank, world, port, n, dtype, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,n", [(2, 6), (4, 7)])
+@pytest.mark.parametrize("world,n,via_planner", [(2, 6, False), (4, 7, False), (2, 8, True), (4, 9, True)])
 @pytest.mark.parametrize("dtype", ["complex128", "complex64"])
-def test_distributed_state_matches_single_state(world, n, dtype):
+def test_distributed_state_matches_single_state(world, n, via_planner, dtype):
+    """via_planner: each rank's local segments are lowered by planner.plan_queue (what the B200
+    backend compiles into pass programs) and interpreted in numpy, instead of gate by gate."""
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + (os.getpid() % 2000) + world
-    procs = [ctx.Process(target=_worker, args=(r, world, port, n, dtype, q)) for r in range(world)]
+    port = 29500 + (os.getpid() % 2000) + world + 8 * via_planner
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, dtype, q, via_planner)) for r in range(world)]
     for p in procs:
         p.start()
     results = q.get(timeout=300)
