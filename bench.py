@@ -220,19 +220,6 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------- GPU arm
-def raw_gate_kind(g, nbytes_state):
-    """(kernel class, algorithmic bytes) of a gate the per-gate kernels execute."""
-    from qibojit_b200.backends.b200 import GATE_OPS
-
-    c = len(g.control_qubits)
-    op = GATE_OPS.get(g.__class__.__name__)
-    if op in ("apply_z", "apply_z_pow", "apply_swap"):
-        return ("diag" if op != "apply_swap" else "swap"), 2 * nbytes_state / 2 ** (c + 1)
-    if op == "apply_fsim":
-        return "fsim", 1.5 * nbytes_state / 2 ** c
-    return f"dense{len(g.target_qubits)}" + (f"c{c}" if c else ""), 2 * nbytes_state / 2 ** c
-
-
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -274,34 +261,21 @@ def run_ours(args):
     state = backend.zero_state(nqubits)
     tag = backend._tag(state)
 
-    nlaunch = {}
-    for seg in prog.segments:
-        if seg[0] == "program":
-            a = ctypes.c_int64()
-            _capi.check(lib.qj_program_stats(seg[1], ctypes.byref(a), None, None))
-            nlaunch[id(seg)] = a.value
-
     def step(events=None):
         nonlocal state
         _capi.check(lib.qj_initial_state(h, state.data_ptr(), tag, nqubits))
-        for seg in prog.segments:
-            if seg[0] == "program":
-                for i in range(nlaunch[id(seg)]):
-                    if events is not None:
-                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                        e0.record()
-                    _capi.check(lib.qj_program_run_launch(h, seg[1], state.data_ptr(), i))
-                    if events is not None:
-                        e1.record()
-                        events.append(("pass", 2.0 * nbytes_state, e0, e1))
-            else:
-                if events is not None:
-                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    e0.record()
-                state = seg[1].apply(backend, state, nqubits)
-                if events is not None:
-                    e1.record()
-                    events.append(raw_gate_kind(seg[1], nbytes_state) + (e0, e1))
+        if events is None:
+            state = prog.run(state)
+            return
+
+        def timer(kind, frac, fn):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            events.append((kind, 2.0 * nbytes_state * frac, e0, e1))
+
+        state = prog.run_timed(state, timer)
 
     for _ in range(args.warmup):
         step()

@@ -61,14 +61,16 @@ struct Lay<float> {
 
 // dispatch codes
 enum {
-    C_DENSE1C = 0,    // + slot
-    C_DENSE1R = 8,    // + slot (real matrix)
-    C_PERM1 = 16,     // + slot (X)
-    C_DENSE2 = 24,    // + pair index (a < b): b (b - 1) / 2 + a
-    C_PERM2 = 40,     // + pair index (SWAP)
-    C_DENSE1X = 50,   // + slot (real diagonal, imaginary off-diagonal: RX, Y, sqrt-X up to a phase)
-    C_PHASE = 56,     // product of per-thread table look-ups, one complex multiply of the selected elements
-    C_DIAGN = 60,     // general: one look-up per element
+    // one-target gates on a SET of register slots (h0.y >> 16 = slot mask, one matrix per slot in
+    // ascending slot order): consecutive gates of one kind on different slots cost one dispatch
+    C_GROUP1C = 0,    // complex 2x2 (8 scalars each)
+    C_GROUP1R = 1,    // real 2x2 (4 scalars)
+    C_GROUP1X = 2,    // real diagonal, imaginary off-diagonal: RX, Y, sqrt-X up to a phase (4 scalars)
+    C_PERM1 = 3,      // + slot (X)
+    C_DENSE2 = 8,     // + pair index (a < b): b (b - 1) / 2 + a
+    C_PERM2 = 18,     // + pair index (SWAP)
+    C_PHASE = 28,     // product of per-thread table look-ups, one complex multiply of the selected elements
+    C_DIAGN = 29,     // general: one look-up per element
 };
 
 // element selection of a C_PHASE op (which of a thread's register amplitudes the phase multiplies)
@@ -181,6 +183,16 @@ __device__ __forceinline__ void op_dense1(Cx<T> (&x)[Lay<T>::N], const uint4 *pa
             }
         }
     }
+}
+
+template <typename T, int KIND>
+__device__ __forceinline__ void op_group1(Cx<T> (&x)[Lay<T>::N], const uint4 *pay, uint32_t slots, uint32_t emask) {
+    constexpr int NU = ((KIND == 0) ? 8 : 4) * sizeof(T) / 16;   // units per matrix
+    if (slots & 1u) { op_dense1<T, 0, KIND>(x, pay, emask); pay += NU; }
+    if (slots & 2u) { op_dense1<T, 1, KIND>(x, pay, emask); pay += NU; }
+    if (slots & 4u) { op_dense1<T, 2, KIND>(x, pay, emask); pay += NU; }
+    if (slots & 8u) { op_dense1<T, 3, KIND>(x, pay, emask); pay += NU; }
+    if (slots & 16u) { op_dense1<T, 4, KIND>(x, pay, emask); }
 }
 
 // two-target gate: matrix-index bit 0 <-> slot A, bit 1 <-> slot B (A < B)
@@ -375,8 +387,9 @@ k_pass(Cx<T> *__restrict__ state, const __grid_constant__ PassGeom pg, const uin
     int32_t *const s_outer = reinterpret_cast<int32_t *>(s_runoff + (1 << pg.nh));
     uint4 *const gvec = reinterpret_cast<uint4 *>(state);
 
-    for (int i = tid; i < pg.blob_units; i += kThreads) prog[i] = __ldg(blob + i);
-    for (int run = tid; run < (1 << pg.nh); run += kThreads) {
+    const int nthr = int(blockDim.x);
+    for (int i = tid; i < pg.blob_units; i += nthr) prog[i] = __ldg(blob + i);
+    for (int run = tid; run < (1 << pg.nh); run += nthr) {
         int64_t off = 0;
         for (int b = 0; b < pg.nh; b++) off |= int64_t((run >> b) & 1) << (pg.hibit[b] - VS);
         s_runoff[run] = off;
@@ -387,7 +400,7 @@ k_pass(Cx<T> *__restrict__ state, const __grid_constant__ PassGeom pg, const uin
     const uint4 *const rounds = prog + hdr.z;
     const uint4 *const outers = prog + hdr.w;
 
-    const bool live = tid < (1 << (Tv - kVecRegBits));
+    // (the launch uses exactly one thread per 16 vectors of the tile: every thread is live)
 
     for (int64_t tile_id = blockIdx.x; tile_id < pg.ntiles; tile_id += gridDim.x) {
         // tile base: insert zeros at the high local bits
@@ -401,10 +414,10 @@ k_pass(Cx<T> *__restrict__ state, const __grid_constant__ PassGeom pg, const uin
         const int64_t base_vec = base_amp >> VS;
 
         // ---- load (asynchronous copies straight into the swizzled tile)
-        for (int lv = tid; lv < nvec; lv += kThreads)
+        for (int lv = tid; lv < nvec; lv += nthr)
             cp_async16(tilev + swz_vec(uint32_t(lv)), gvec + base_vec + s_runoff[lv >> rv] + (lv & rvmask));
         // per-op tile constants: outer control predicate and outer part of the table index
-        for (int m = tid; m < nouter; m += kThreads) {
+        for (int m = tid; m < nouter; m += nthr) {
             const uint4 o0 = outers[2 * m], o1 = outers[2 * m + 1];
             const uint64_t ocmask = uint64_t(o0.x) | (uint64_t(o0.y) << 32);
             int32_t v = 0;
@@ -429,7 +442,7 @@ k_pass(Cx<T> *__restrict__ state, const __grid_constant__ PassGeom pg, const uin
 #pragma unroll 1
         for (int rd = 0; rd < nrounds; rd++) {
             const uint4 r0 = rounds[3 * rd], r1 = rounds[3 * rd + 1], r2 = rounds[3 * rd + 2];
-            if (live) {
+            {
                 uint32_t vd[4] = {r0.z & 0xffffu, r0.z >> 16, r0.w & 0xffffu, r0.w >> 16};
                 const uint32_t tdw[4] = {r1.x, r1.y, r1.z, r1.w};
                 uint32_t S = 0, base = 0;
@@ -455,39 +468,39 @@ k_pass(Cx<T> *__restrict__ state, const __grid_constant__ PassGeom pg, const uin
                     }
                 }
 
+                // The op loop has warp-uniform control flow only: a thread whose predicate fails
+                // (control bit outside the registers is 0, outer control not satisfied) runs the
+                // same op with an empty element mask / a unit phase instead of branching around it.
                 const uint4 *op = prog + r0.x;
-                const int nops = int(r0.y);
+                const uint4 *const op_end = op + r0.y;   // r0.y = units of this round's op stream
 #pragma unroll 1
-                for (int i = 0; i < nops; i++) {
+                while (op != op_end) {
                     const uint4 h0 = op[0], h1 = op[1];
                     const uint4 *pay = op + 2;
                     op += h0.x >> 16;
-                    const uint32_t code = h0.x & 0xffffu, emask = h0.w;
+                    const uint32_t code = h0.x & 0xffffu;
+                    uint32_t emask = h0.w;
                     int oi = 0;
-                    if (code != C_PHASE) {  // (a phase group keeps the predicates per table)
+                    if (code != C_PHASE && (h0.z != 0u || (h0.y & 0xffffu) != 0xffffu)) {   // predicated op
                         const uint32_t oslot = h0.y & 0xffffu, tmask = h0.z;
+                        bool ok = (base & tmask) == tmask;
                         if (oslot != 0xffffu) {
                             oi = s_outer[oslot];
-                            if (oi < 0) continue;                   // outer control not satisfied by this tile
+                            ok = ok && oi >= 0;
+                            oi = max(oi, 0);
                         }
-                        if ((base & tmask) != tmask) continue;      // tile-local control outside the registers
+                        emask = ok ? emask : 0u;
                     }
                     switch (code) {
-#define QJ_D1C(A) op_dense1<T, A, 0>(x, pay, emask)
-#define QJ_D1R(A) op_dense1<T, A, 1>(x, pay, emask)
-#define QJ_D1X(A) op_dense1<T, A, 2>(x, pay, emask)
 #define QJ_P1(A) op_perm1<T, A>(x, emask)
 #define QJ_D2(A, B) op_dense2<T, A, B>(x, pay, emask)
 #define QJ_P2(A, B) op_perm2<T, A, B>(x, emask)
-                        QJ_SLOT_CASES(C_DENSE1C, QJ_D1C)
-                        QJ_SLOT_CASES(C_DENSE1R, QJ_D1R)
-                        QJ_SLOT_CASES(C_DENSE1X, QJ_D1X)
+                        case C_GROUP1C: op_group1<T, 0>(x, pay, h0.y >> 16, emask); break;
+                        case C_GROUP1R: op_group1<T, 1>(x, pay, h0.y >> 16, emask); break;
+                        case C_GROUP1X: op_group1<T, 2>(x, pay, h0.y >> 16, emask); break;
                         QJ_SLOT_CASES(C_PERM1, QJ_P1)
                         QJ_PAIR_CASES(C_DENSE2, QJ_D2)
                         QJ_PAIR_CASES(C_PERM2, QJ_P2)
-#undef QJ_D1C
-#undef QJ_D1R
-#undef QJ_D1X
 #undef QJ_P1
 #undef QJ_D2
 #undef QJ_P2
@@ -501,7 +514,6 @@ k_pass(Cx<T> *__restrict__ state, const __grid_constant__ PassGeom pg, const uin
                             Cx<T> ph;
                             ph.re = T(1); ph.im = T(0);
                             uint32_t sg = 0;
-                            bool any = false;
 #pragma unroll 1
                             for (int t = 0; t < ntab; t++) {
                                 const uint4 d0 = d[0], d1 = d[1];
@@ -510,11 +522,11 @@ k_pass(Cx<T> *__restrict__ state, const __grid_constant__ PassGeom pg, const uin
                                 const uint4 *const dx = d + 2;
                                 d += (nf > 5) ? 3 : 2;
                                 int idx = 0;
+                                bool ok = (base & d0.z) == d0.z;             // tile-local control outside the registers
                                 if (osl != 0xffffu) {
                                     idx = s_outer[osl];
-                                    if (idx < 0) continue;                   // outer control not satisfied
+                                    ok = ok && idx >= 0;                     // outer control
                                 }
-                                if ((base & d0.z) != d0.z) continue;         // tile-local control outside the registers
                                 if (nf > 0) idx |= field_of(base, d0.w);
                                 if (nf > 1) {
                                     idx |= field_of(base, d1.x);
@@ -529,24 +541,20 @@ k_pass(Cx<T> *__restrict__ state, const __grid_constant__ PassGeom pg, const uin
                                         if (nf > 8) idx |= field_of(base, d2.w);
                                     }
                                 }
-                                const Cx<T> z = ldg_cx(tables + d0.x + idx);
+                                Cx<T> z = ldg_cx(tables + d0.x + (ok ? idx : 0));
+                                if (!ok) { z.re = T(1); z.im = T(0); }
                                 if (allsign) {
                                     sg ^= sign_of(z.re);
-                                } else if (!any) {
+                                } else if (t == 0) {
                                     ph = z;
                                 } else {
                                     const T nr = fma(ph.re, z.re, -(ph.im * z.im));
                                     ph.im = fma(ph.re, z.im, ph.im * z.re);
                                     ph.re = nr;
                                 }
-                                any = true;
                             }
-                            if (!any) break;
-                            if (allsign) {
-                                if (sg) phase_apply<T, true>(x, sel, emask, T(0), T(0), sg);
-                            } else {
-                                phase_apply<T, false>(x, sel, emask, ph.re, ph.im, 0u);
-                            }
+                            if (allsign) phase_apply<T, true>(x, sel, emask, T(0), T(0), sg);
+                            else phase_apply<T, false>(x, sel, emask, ph.re, ph.im, 0u);
                         } break;
                         default: {  // C_DIAGN: table index = outer part | fields of the base | element part
                             const int nf = int(h0.y >> 16);
@@ -574,18 +582,14 @@ k_pass(Cx<T> *__restrict__ state, const __grid_constant__ PassGeom pg, const uin
                                     if ((emask >> e) & 1u) ph[k] = ldg_cx(tab + idx);
                                 }
 #pragma unroll
-                                for (int k = 0; k < 8; k++) {
-                                    const int e = e8 + k;
-                                    if (!((emask >> e) & 1u)) continue;
-                                    const Cx<T> v = x[e];
-                                    x[e].re = fma(ph[k].re, v.re, -ph[k].im * v.im);
-                                    x[e].im = fma(ph[k].re, v.im, ph[k].im * v.re);
-                                }
+                                for (int k = 0; k < 8; k++) cmul_inplace<T>(x[e8 + k], ph[k].re, ph[k].im);
                             }
                         }
                     }
                 }
 
+                // the 16 scatter addresses are recomputed, not kept live across the op loop
+                asm volatile("" : "+r"(S), "+r"(vd[0]), "+r"(vd[1]), "+r"(vd[2]), "+r"(vd[3]));
 #pragma unroll
                 for (int v = 0; v < 16; v++) {
                     const uint32_t off = S ^ ((v & 1) ? vd[0] : 0u) ^ ((v & 2) ? vd[1] : 0u) ^
@@ -606,16 +610,16 @@ k_pass(Cx<T> *__restrict__ state, const __grid_constant__ PassGeom pg, const uin
 
         // ---- store the tile
         constexpr int UNR = 8;
-        for (int v0 = 0; v0 < nvec; v0 += kThreads * UNR) {
+        for (int v0 = 0; v0 < nvec; v0 += nthr * UNR) {
             uint4 q[UNR];
 #pragma unroll
             for (int u = 0; u < UNR; u++) {
-                const int lv = v0 + u * kThreads + tid;
+                const int lv = v0 + u * nthr + tid;
                 if (lv < nvec) q[u] = tilev[swz_vec(uint32_t(lv))];
             }
 #pragma unroll
             for (int u = 0; u < UNR; u++) {
-                const int lv = v0 + u * kThreads + tid;
+                const int lv = v0 + u * nthr + tid;
                 if (lv < nvec) gvec[base_vec + s_runoff[lv >> rv] + (lv & rvmask)] = q[u];
             }
         }
@@ -884,6 +888,7 @@ extern "C" int qj_program_create(qj_handle *h, int dtype, int nqubits, const qj_
                 bool sign;
             };
             std::vector<PendingSlice> pending;
+            std::vector<size_t> group_run;  // r_ops indices of the trailing run of plain one-target groups
             auto select_code = [&](uint32_t emask) -> uint32_t {
                 const uint32_t full = (N == 32) ? 0xffffffffu : 0xffffu;
                 if (emask == full) return SEL_ALL;
@@ -901,6 +906,7 @@ extern "C" int qj_program_create(qj_handle *h, int dtype, int nqubits, const qj_
                 return SEL_MASK;
             };
             auto flush_pending = [&]() {
+                if (!pending.empty()) group_run.clear();
                 std::vector<bool> done(pending.size(), false);
                 for (size_t i = 0; i < pending.size(); i++) {
                     if (done[i]) continue;
@@ -982,19 +988,53 @@ extern "C" int qj_program_create(qj_handle *h, int dtype, int nqubits, const qj_
                         const bool is_x = real && m[0] == 0.0 && m[1] == 1.0 && m[2] == 1.0 && m[3] == 0.0;
                         if (is_x) {
                             push_op(C_PERM1 + sl[0], oslot, 0, tmask, cmask_e, 0, nullptr, payload);
-                        } else if (real) {
-                            enc.push_scalars(payload, {m[0].real(), m[1].real(), m[2].real(), m[3].real()});
-                            push_op(C_DENSE1R + sl[0], oslot, 0, tmask, cmask_e, 0, nullptr, payload);
-                        } else if (m[0].imag() == 0.0 && m[3].imag() == 0.0 && m[1].real() == 0.0 && m[2].real() == 0.0) {
-                            enc.push_scalars(payload, {m[0].real(), m[1].imag(), m[2].imag(), m[3].real()});
-                            push_op(C_DENSE1X + sl[0], oslot, 0, tmask, cmask_e, 0, nullptr, payload);
+                            group_run.clear();
                         } else {
-                            std::vector<double> s;
-                            for (const cd &z : m) { s.push_back(z.real()); s.push_back(z.imag()); }
-                            enc.push_scalars(payload, s);
-                            push_op(C_DENSE1C + sl[0], oslot, 0, tmask, cmask_e, 0, nullptr, payload);
+                            uint32_t code;
+                            if (real) {
+                                code = C_GROUP1R;
+                                enc.push_scalars(payload, {m[0].real(), m[1].real(), m[2].real(), m[3].real()});
+                            } else if (m[0].imag() == 0.0 && m[3].imag() == 0.0 && m[1].real() == 0.0 && m[2].real() == 0.0) {
+                                code = C_GROUP1X;
+                                enc.push_scalars(payload, {m[0].real(), m[1].imag(), m[2].imag(), m[3].real()});
+                            } else {
+                                code = C_GROUP1C;
+                                std::vector<double> sc;
+                                for (const cd &z : m) { sc.push_back(z.real()); sc.push_back(z.imag()); }
+                                enc.push_scalars(payload, sc);
+                            }
+                            const uint32_t full = (N == 32) ? 0xffffffffu : 0xffffu;
+                            const bool plain = cmask_e == full && tmask == 0 && oslot == 0xffff;
+                            // plain gates on different slots commute: merge into the nearest earlier
+                            // plain group of the same kind, unless a group in between holds this slot
+                            bool merged = false;
+                            if (plain) {
+                                for (size_t gi = group_run.size(); gi-- > 0 && !merged;) {
+                                    const size_t at = group_run[gi];
+                                    const uint32_t gslots = r_ops[at].w[1] >> 16;
+                                    if ((gslots >> sl[0]) & 1u) break;
+                                    if ((r_ops[at].w[0] & 0xffffu) != code) continue;
+                                    uint32_t below = 0;
+                                    for (int q = 0; q < sl[0]; q++) below += (gslots >> q) & 1u;
+                                    const size_t pos = at + 2 + size_t(below) * payload.size();
+                                    r_ops.insert(r_ops.begin() + pos, payload.begin(), payload.end());
+                                    r_ops[at].w[0] += uint32_t(payload.size()) << 16;
+                                    r_ops[at].w[1] |= (1u << sl[0]) << 16;
+                                    for (size_t gj = gi + 1; gj < group_run.size(); gj++) group_run[gj] += payload.size();
+                                    merged = true;
+                                }
+                            } else {
+                                group_run.clear();
+                            }
+                            if (!merged) {
+                                const size_t at = r_ops.size();
+                                push_op(code, oslot, 0, tmask, cmask_e, 0, nullptr, payload);
+                                r_ops[at].w[1] |= (1u << sl[0]) << 16;
+                                if (plain) group_run.push_back(at);
+                            }
                         }
                     } else {
+                        group_run.clear();
                         int a = sl[0], b = sl[1];
                         if (a > b) {  // canonical slot order: exchange the matrix-index bits
                             std::vector<cd> t(16);
@@ -1103,6 +1143,7 @@ extern "C" int qj_program_create(qj_handle *h, int dtype, int nqubits, const qj_
                     } else {
                         // general table: index = thread fields | outer bits | register bits
                         flush_pending();
+                        group_run.clear();
                         if (nf > 7) return bail("op: diagonal table needs too many bit fields");
                         std::vector<cd> t(size_t(1) << nb);
                         for (int a = 0; a < (1 << k); a++)
@@ -1152,7 +1193,7 @@ extern "C" int qj_program_create(qj_handle *h, int dtype, int nqubits, const qj_
                 Unit u0, u1, u2;
                 memset(&u0, 0, sizeof(u0)); memset(&u1, 0, sizeof(u1)); memset(&u2, 0, sizeof(u2));
                 u0.w[0] = uint32_t(op_units.size());   // relative to the op stream; rebased in close_launch
-                u0.w[1] = uint32_t(r_nops);
+                u0.w[1] = uint32_t(r_ops.size());   // units of the round's op stream
                 u0.w[2] = vd[0] | (vd[1] << 16); u0.w[3] = vd[2] | (vd[3] << 16);
                 for (size_t kbit = 0; kbit < tq.size() && kbit < 8; kbit++) {
                     const uint32_t td = swz_vec(1u << tq[kbit]) << 4;
@@ -1217,10 +1258,14 @@ int launch_pass(qj_handle *h, const qj_program *p, void *state, const qj_program
         QJ_CUDA_OK(cudaFuncSetAttribute(k_pass<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 << 10));
         configured = true;
     }
-    // two CTAs per SM when the tile is large; small tiles: more CTAs per SM
-    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t(224) << 10) / (L.smem + 1024)));
-    const unsigned grid = (unsigned)std::min<int64_t>(L.geom.ntiles, int64_t(h->sm_count) * std::min(per_sm, 2));
-    k_pass<T><<<grid, kThreads, L.smem, h->stream>>>(
+    // one thread per 16 vectors of the tile (at most 256); 128 registers per thread allow 512
+    // resident threads per SM: two 64 KiB tiles or four 32 KiB tiles in different phases
+    const int VS = (sizeof(T) == 8) ? 0 : 1;
+    const int threads = std::max(1, std::min(kThreads, (1 << (L.geom.T - VS)) >> kVecRegBits));
+    const int by_smem = (int)std::max<size_t>(1, (size_t(224) << 10) / (L.smem + 1024));
+    const int per_sm = std::max(1, std::min(by_smem, 512 / threads));
+    const unsigned grid = (unsigned)std::min<int64_t>(L.geom.ntiles, int64_t(h->sm_count) * per_sm);
+    k_pass<T><<<grid, threads, L.smem, h->stream>>>(
         reinterpret_cast<Cx<T> *>(state), L.geom, reinterpret_cast<const uint4 *>(p->d_blob) + L.blob_off,
         reinterpret_cast<const Cx<T> *>(p->d_tables));
     h->launches++;

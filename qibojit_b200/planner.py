@@ -397,6 +397,35 @@ class Program:
                 state = seg[1].apply(b, state, self.nqubits)
         return state
 
+    def run_timed(self, state, timer):
+        """Like run(), but every kernel launch goes through ``timer(kind, fraction, fn)`` where
+        `fraction` is the launch's algorithmic traffic in units of one full read+write of the
+        state -- bench.py brackets `fn` with CUDA events."""
+        from .backends.b200 import GATE_OPS
+
+        b = self.backend
+        for seg in self.segments:
+            if seg[0] == "program":
+                a = ctypes.c_int64()
+                _capi.check(b._lib.qj_program_stats(seg[1], ctypes.byref(a), None, None))
+                for i in range(a.value):
+                    timer("pass", 1.0, lambda i=i: _capi.check(
+                        b._lib.qj_program_run_launch(b._handle(), seg[1], state.data_ptr(), i)))
+            else:
+                g = seg[1]
+                c = len(g.control_qubits)
+                op = getattr(g, "op", None) or GATE_OPS.get(g.__class__.__name__)
+                if op in ("apply_z", "apply_z_pow", "apply_swap"):
+                    kind, frac = ("swap" if op == "apply_swap" else "diag"), 2.0 ** -(c + 1)
+                elif op == "apply_fsim":
+                    kind, frac = "fsim", 0.75 * 2.0 ** -c
+                else:
+                    kind, frac = f"dense{len(g.target_qubits)}" + (f"c{c}" if c else ""), 2.0 ** -c
+                out = []
+                timer(kind, frac, lambda: out.append(g.apply(b, state, self.nqubits)))
+                state = out[0]
+        return state
+
     def stats(self):
         """{'launches', 'rounds', 'micro_ops', 'raw_gates'} summed over the segments."""
         out = dict(launches=0, rounds=0, micro_ops=0, raw_gates=0, passes=len(self.passes))
