@@ -88,10 +88,13 @@ struct PassGeom {
     int pos[QJ_MAX_QUBITS];
     int64_t ntiles;
     int blob_units;        // program image, 16-byte units
+    int nH;                // per-tile phase factors (outer-only parts of the phase groups)
 };
 
 // ---- program image (16-byte units) -------------------------------------------------------------
 // unit 0            : {nrounds, nouter, off_rounds, off_outer}
+// unit 1            : {nH, off_H, 0, 0}
+// H entries, 4 units: {ntab, 0, 0, 0} {table, oslot, table, oslot} x 3   (product of <= 6 outer-indexed look-ups)
 // rounds, 3 units   : {first_unit, nops, vd0 | vd1 << 16, vd2 | vd3 << 16}
 //                     {td[0..7] as uint16}  {tpos[0..7] as uint8, 0, 0}
 // outers, 2 units   : {ocmask lo, ocmask hi, nbits, src[0..3]} {src[4..11], dst packed 4 bit x 12 ...}
@@ -327,14 +330,15 @@ __device__ __forceinline__ void phase_apply(Cx<T> (&x)[Lay<T>::N], uint32_t sel,
 __device__ __forceinline__ uint32_t sign_of(double v) { return uint32_t(__double2hiint(v)) & 0x80000000u; }
 __device__ __forceinline__ uint32_t sign_of(float v) { return __float_as_uint(v) & 0x80000000u; }
 
+// phase-table / factor loads: read-only path, kept in L1 against the streaming tile traffic
 __device__ __forceinline__ Cx<double> ldg_cx(const Cx<double> *p) {
-    const double2 v = __ldg(reinterpret_cast<const double2 *>(p));
-    Cx<double> c; c.re = v.x; c.im = v.y;
+    Cx<double> c;
+    asm("ld.global.nc.L1::evict_last.v2.f64 {%0, %1}, [%2];" : "=d"(c.re), "=d"(c.im) : "l"(p));
     return c;
 }
 __device__ __forceinline__ Cx<float> ldg_cx(const Cx<float> *p) {
-    const float2 v = __ldg(reinterpret_cast<const float2 *>(p));
-    Cx<float> c; c.re = v.x; c.im = v.y;
+    Cx<float> c;
+    asm("ld.global.nc.L1::evict_last.v2.f32 {%0, %1}, [%2];" : "=f"(c.re), "=f"(c.im) : "l"(p));
     return c;
 }
 
@@ -348,7 +352,26 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
                  "l"(gmem_src)
                  : "memory");
 }
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// tile constant of outer slot m: -1 when its outer controls are not satisfied by this tile, else
+// the outer part of the table index
+__device__ __forceinline__ int32_t outer_value(const uint4 *outers, int m, int64_t base_amp) {
+    const uint4 o0 = outers[2 * m], o1 = outers[2 * m + 1];
+    const uint64_t ocmask = uint64_t(o0.x) | (uint64_t(o0.y) << 32);
+    if ((uint64_t(base_amp) & ocmask) != ocmask) return -1;
+    int32_t v = 0;
+    const int nb = int(o0.z);
+    const uint32_t srcw[3] = {o0.w, o1.x, o1.y};
+    const uint32_t dstw[2] = {o1.z, o1.w};
+    for (int b = 0; b < nb; b++) {
+        const int src = (srcw[b >> 2] >> ((b & 3) * 8)) & 255;
+        const int dst = (dstw[b >> 3] >> ((b & 7) * 4)) & 15;
+        v |= int32_t((base_amp >> src) & 1) << dst;
+    }
+    return v;
+}
 
 #define QJ_SLOT_CASES(CODE, CALL)                  \
     case CODE + 0: { CALL(0); } break;             \
@@ -383,7 +406,8 @@ k_pass(Cx<T> *__restrict__ state, const __grid_constant__ PassGeom pg, const uin
     const int rvmask = (1 << rv) - 1;
     uint4 *const tilev = reinterpret_cast<uint4 *>(smem_raw);
     uint4 *const prog = tilev + nvec;
-    int64_t *const s_runoff = reinterpret_cast<int64_t *>(prog + pg.blob_units);   // in vectors
+    uint4 *const s_H = prog + pg.blob_units;                                        // one 16-byte slot per factor
+    int64_t *const s_runoff = reinterpret_cast<int64_t *>(s_H + pg.nH);             // in vectors
     int32_t *const s_outer = reinterpret_cast<int32_t *>(s_runoff + (1 << pg.nh));
     uint4 *const gvec = reinterpret_cast<uint4 *>(state);
 
@@ -399,8 +423,13 @@ k_pass(Cx<T> *__restrict__ state, const __grid_constant__ PassGeom pg, const uin
     const int nrounds = int(hdr.x), nouter = int(hdr.y);
     const uint4 *const rounds = prog + hdr.z;
     const uint4 *const outers = prog + hdr.w;
+    const int nH = int(prog[1].x);
+    const uint4 *const hents = prog + prog[1].y;
 
     // (the launch uses exactly one thread per 16 vectors of the tile: every thread is live)
+    const bool fast_io = nthr >= 8 && nthr >= (1 << rv) && nvec == 16 * nthr;   // 16 vectors per thread
+    const uint32_t sw_t = swz_vec(uint32_t(tid));
+    const int lane_off = tid & rvmask, run_t = tid >> rv, runs_per_iter = nthr >> rv;
 
     for (int64_t tile_id = blockIdx.x; tile_id < pg.ntiles; tile_id += gridDim.x) {
         // tile base: insert zeros at the high local bits
@@ -414,26 +443,36 @@ k_pass(Cx<T> *__restrict__ state, const __grid_constant__ PassGeom pg, const uin
         const int64_t base_vec = base_amp >> VS;
 
         // ---- load (asynchronous copies straight into the swizzled tile)
-        for (int lv = tid; lv < nvec; lv += nthr)
-            cp_async16(tilev + swz_vec(uint32_t(lv)), gvec + base_vec + s_runoff[lv >> rv] + (lv & rvmask));
+        if (fast_io) {
+            // vector u * nthr + tid: the swizzle is XOR-linear and nthr a multiple of the run length,
+            // so the per-thread and the per-iteration (warp-uniform) parts separate
+            const uint4 *const gsrc = gvec + base_vec + lane_off;
+#pragma unroll
+            for (int u = 0; u < 16; u++)
+                cp_async16(tilev + (sw_t ^ swz_vec(uint32_t(u * nthr))), gsrc + s_runoff[run_t + u * runs_per_iter]);
+        } else {
+            for (int lv = tid; lv < nvec; lv += nthr)
+                cp_async16(tilev + swz_vec(uint32_t(lv)), gvec + base_vec + s_runoff[lv >> rv] + (lv & rvmask));
+        }
         // per-op tile constants: outer control predicate and outer part of the table index
-        for (int m = tid; m < nouter; m += nthr) {
-            const uint4 o0 = outers[2 * m], o1 = outers[2 * m + 1];
-            const uint64_t ocmask = uint64_t(o0.x) | (uint64_t(o0.y) << 32);
-            int32_t v = 0;
-            if ((uint64_t(base_amp) & ocmask) != ocmask) {
-                v = -1;
-            } else {
-                const int nb = int(o0.z);
-                const uint32_t srcw[3] = {o0.w, o1.x, o1.y};
-                const uint32_t dstw[2] = {o1.z, o1.w};
-                for (int b = 0; b < nb; b++) {
-                    const int src = (srcw[b >> 2] >> ((b & 3) * 8)) & 255;
-                    const int dst = (dstw[b >> 3] >> ((b & 7) * 4)) & 15;
-                    v |= int32_t((base_amp >> src) & 1) << dst;
-                }
+        for (int m = tid; m < nouter; m += nthr) s_outer[m] = outer_value(outers, m, base_amp);
+        // per-tile phase factors: product of the outer-indexed look-ups of a phase group
+        for (int m = tid; m < nH; m += nthr) {
+            const uint4 *he = hents + 4 * m;
+            const int ntab = int(he[0].x);
+            Cx<T> acc;
+            acc.re = T(1); acc.im = T(0);
+            for (int t = 0; t < ntab; t++) {
+                const uint4 u = he[1 + (t >> 1)];
+                const uint32_t table = (t & 1) ? u.z : u.x, osl = (t & 1) ? u.w : u.y;
+                const int32_t v = outer_value(outers, int(osl), base_amp);
+                if (v < 0) continue;
+                const Cx<T> z = ldg_cx(tables + table + v);
+                const T nr = fma(acc.re, z.re, -(acc.im * z.im));
+                acc.im = fma(acc.re, z.im, acc.im * z.re);
+                acc.re = nr;
             }
-            s_outer[m] = v;
+            *reinterpret_cast<Cx<T> *>(s_H + m) = acc;
         }
         cp_async_wait_all();
         __syncthreads();
@@ -442,6 +481,7 @@ k_pass(Cx<T> *__restrict__ state, const __grid_constant__ PassGeom pg, const uin
 #pragma unroll 1
         for (int rd = 0; rd < nrounds; rd++) {
             const uint4 r0 = rounds[3 * rd], r1 = rounds[3 * rd + 1], r2 = rounds[3 * rd + 2];
+            if (r2.z != 0xffffffffu) prefetch_l1(tables + r2.z + tid);         // G of the round's first phase group
             {
                 uint32_t vd[4] = {r0.z & 0xffffu, r0.z >> 16, r0.w & 0xffffu, r0.w >> 16};
                 const uint32_t tdw[4] = {r1.x, r1.y, r1.z, r1.w};
@@ -458,13 +498,13 @@ k_pass(Cx<T> *__restrict__ state, const __grid_constant__ PassGeom pg, const uin
                 for (int v = 0; v < 16; v++) {
                     const uint32_t off = S ^ ((v & 1) ? vd[0] : 0u) ^ ((v & 2) ? vd[1] : 0u) ^
                                          ((v & 4) ? vd[2] : 0u) ^ ((v & 8) ? vd[3] : 0u);
-                    const uint4 q = *reinterpret_cast<const uint4 *>(smem_raw + off);
                     if constexpr (sizeof(T) == 8) {
-                        x[v].re = __hiloint2double(int(q.y), int(q.x));
-                        x[v].im = __hiloint2double(int(q.w), int(q.z));
+                        const double2 q = *reinterpret_cast<const double2 *>(smem_raw + off);
+                        x[v].re = q.x; x[v].im = q.y;
                     } else {
-                        x[2 * v].re = __uint_as_float(q.x); x[2 * v].im = __uint_as_float(q.y);
-                        x[2 * v + 1].re = __uint_as_float(q.z); x[2 * v + 1].im = __uint_as_float(q.w);
+                        const float4 q = *reinterpret_cast<const float4 *>(smem_raw + off);
+                        x[2 * v].re = q.x; x[2 * v].im = q.y;
+                        x[2 * v + 1].re = q.z; x[2 * v + 1].im = q.w;
                     }
                 }
 
@@ -480,6 +520,7 @@ k_pass(Cx<T> *__restrict__ state, const __grid_constant__ PassGeom pg, const uin
                     op += h0.x >> 16;
                     const uint32_t code = h0.x & 0xffffu;
                     uint32_t emask = h0.w;
+                    if (code != C_DIAGN && h1.z != 0xffffffffu) prefetch_l1(tables + h1.z + tid);   // G of the next phase group
                     int oi = 0;
                     if (code != C_PHASE && (h0.z != 0u || (h0.y & 0xffffu) != 0xffffu)) {   // predicated op
                         const uint32_t oslot = h0.y & 0xffffu, tmask = h0.z;
@@ -514,43 +555,79 @@ k_pass(Cx<T> *__restrict__ state, const __grid_constant__ PassGeom pg, const uin
                             Cx<T> ph;
                             ph.re = T(1); ph.im = T(0);
                             uint32_t sg = 0;
-#pragma unroll 1
-                            for (int t = 0; t < ntab; t++) {
-                                const uint4 d0 = d[0], d1 = d[1];
-                                const int nf = int(d0.y & 0xffffu);
-                                const uint32_t osl = d0.y >> 16;
-                                const uint4 *const dx = d + 2;
-                                d += (nf > 5) ? 3 : 2;
-                                int idx = 0;
-                                bool ok = (base & d0.z) == d0.z;             // tile-local control outside the registers
-                                if (osl != 0xffffu) {
-                                    idx = s_outer[osl];
-                                    ok = ok && idx >= 0;                     // outer control
-                                }
-                                if (nf > 0) idx |= field_of(base, d0.w);
-                                if (nf > 1) {
-                                    idx |= field_of(base, d1.x);
-                                    if (nf > 2) idx |= field_of(base, d1.y);
-                                    if (nf > 3) idx |= field_of(base, d1.z);
-                                    if (nf > 4) idx |= field_of(base, d1.w);
-                                    if (nf > 5) {
-                                        const uint4 d2 = dx[0];
-                                        idx |= field_of(base, d2.x);
-                                        if (nf > 6) idx |= field_of(base, d2.y);
-                                        if (nf > 7) idx |= field_of(base, d2.z);
-                                        if (nf > 8) idx |= field_of(base, d2.w);
-                                    }
-                                }
-                                Cx<T> z = ldg_cx(tables + d0.x + (ok ? idx : 0));
-                                if (!ok) { z.re = T(1); z.im = T(0); }
+                            bool have = false;
+                            constexpr int KB = 4;   // look-ups in flight
+                            // h1.x: per-thread factor G[tid] (thread-only part, precomputed on the host:
+                            // a thread's tile position is the same in every tile); h1.y: per-tile factor
+                            if (h1.x != 0xffffffffu) {
+                                const Cx<T> z = ldg_cx(tables + h1.x + tid);
+                                if (allsign) sg ^= sign_of(z.re);
+                                else ph = z;
+                                have = true;
+                            }
+                            if (h1.y != 0xffffffffu) {
+                                const Cx<T> z = *reinterpret_cast<const Cx<T> *>(s_H + h1.y);
                                 if (allsign) {
                                     sg ^= sign_of(z.re);
-                                } else if (t == 0) {
+                                } else if (!have) {
                                     ph = z;
                                 } else {
                                     const T nr = fma(ph.re, z.re, -(ph.im * z.im));
                                     ph.im = fma(ph.re, z.im, ph.im * z.re);
                                     ph.re = nr;
+                                }
+                                have = true;
+                            }
+#pragma unroll 1
+                            for (int t0 = 0; t0 < ntab; t0 += KB) {
+                                Cx<T> z[KB];
+#pragma unroll
+                                for (int k = 0; k < KB; k++) {
+                                    z[k].re = T(1); z[k].im = T(0);
+                                    if (t0 + k < ntab) {
+                                        const uint4 d0 = d[0], d1 = d[1];
+                                        const int nf = int(d0.y & 0xffffu);
+                                        const uint32_t osl = d0.y >> 16;
+                                        const uint4 *const dx = d + 2;
+                                        d += (nf > 5) ? 3 : 2;
+                                        int idx = 0;
+                                        bool ok = (base & d0.z) == d0.z;     // tile-local control outside the registers
+                                        if (osl != 0xffffu) {
+                                            idx = s_outer[osl];
+                                            ok = ok && idx >= 0;             // outer control
+                                        }
+                                        {
+                                            if (nf > 0) idx |= field_of(base, d0.w);
+                                            if (nf > 1) {
+                                                idx |= field_of(base, d1.x);
+                                                if (nf > 2) idx |= field_of(base, d1.y);
+                                                if (nf > 3) idx |= field_of(base, d1.z);
+                                                if (nf > 4) idx |= field_of(base, d1.w);
+                                                if (nf > 5) {
+                                                    const uint4 d2 = dx[0];
+                                                    idx |= field_of(base, d2.x);
+                                                    if (nf > 6) idx |= field_of(base, d2.y);
+                                                    if (nf > 7) idx |= field_of(base, d2.z);
+                                                    if (nf > 8) idx |= field_of(base, d2.w);
+                                                }
+                                            }
+                                            if (ok) z[k] = ldg_cx(tables + d0.x + idx);
+                                        }
+                                    }
+                                }
+#pragma unroll
+                                for (int k = 0; k < KB; k++) {
+                                    if (t0 + k >= ntab) break;
+                                    if (allsign) {
+                                        sg ^= sign_of(z[k].re);
+                                    } else if (!have) {
+                                        ph = z[k];
+                                        have = true;
+                                    } else {
+                                        const T nr = fma(ph.re, z[k].re, -(ph.im * z[k].im));
+                                        ph.im = fma(ph.re, z[k].im, ph.im * z[k].re);
+                                        ph.re = nr;
+                                    }
                                 }
                             }
                             if (allsign) phase_apply<T, true>(x, sel, emask, T(0), T(0), sg);
@@ -594,33 +671,42 @@ k_pass(Cx<T> *__restrict__ state, const __grid_constant__ PassGeom pg, const uin
                 for (int v = 0; v < 16; v++) {
                     const uint32_t off = S ^ ((v & 1) ? vd[0] : 0u) ^ ((v & 2) ? vd[1] : 0u) ^
                                          ((v & 4) ? vd[2] : 0u) ^ ((v & 8) ? vd[3] : 0u);
-                    uint4 q;
                     if constexpr (sizeof(T) == 8) {
-                        q.x = uint32_t(__double2loint(x[v].re)); q.y = uint32_t(__double2hiint(x[v].re));
-                        q.z = uint32_t(__double2loint(x[v].im)); q.w = uint32_t(__double2hiint(x[v].im));
+                        *reinterpret_cast<double2 *>(smem_raw + off) = make_double2(x[v].re, x[v].im);
                     } else {
-                        q.x = __float_as_uint(x[2 * v].re); q.y = __float_as_uint(x[2 * v].im);
-                        q.z = __float_as_uint(x[2 * v + 1].re); q.w = __float_as_uint(x[2 * v + 1].im);
+                        *reinterpret_cast<float4 *>(smem_raw + off) =
+                            make_float4(x[2 * v].re, x[2 * v].im, x[2 * v + 1].re, x[2 * v + 1].im);
                     }
-                    *reinterpret_cast<uint4 *>(smem_raw + off) = q;
                 }
             }
             __syncthreads();
         }
 
-        // ---- store the tile
-        constexpr int UNR = 8;
-        for (int v0 = 0; v0 < nvec; v0 += nthr * UNR) {
-            uint4 q[UNR];
+        // ---- store the tile (four vectors in flight per thread)
+        if (fast_io) {
+            uint4 *const gdst = gvec + base_vec + lane_off;
 #pragma unroll
-            for (int u = 0; u < UNR; u++) {
-                const int lv = v0 + u * nthr + tid;
-                if (lv < nvec) q[u] = tilev[swz_vec(uint32_t(lv))];
+            for (int u0 = 0; u0 < 16; u0 += 4) {
+                uint4 q[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) q[k] = tilev[sw_t ^ swz_vec(uint32_t((u0 + k) * nthr))];
+#pragma unroll
+                for (int k = 0; k < 4; k++) gdst[s_runoff[run_t + (u0 + k) * runs_per_iter]] = q[k];
             }
+        } else {
+#pragma unroll 1
+            for (int v0 = tid; v0 < nvec; v0 += 4 * nthr) {
+                uint4 q[4];
 #pragma unroll
-            for (int u = 0; u < UNR; u++) {
-                const int lv = v0 + u * nthr + tid;
-                if (lv < nvec) gvec[base_vec + s_runoff[lv >> rv] + (lv & rvmask)] = q[u];
+                for (int u = 0; u < 4; u++) {
+                    const int lv = v0 + u * nthr;
+                    if (lv < nvec) q[u] = tilev[swz_vec(uint32_t(lv))];
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int lv = v0 + u * nthr;
+                    if (lv < nvec) gvec[base_vec + s_runoff[lv >> rv] + (lv & rvmask)] = q[u];
+                }
             }
         }
         __syncthreads();   // the next tile's asynchronous copies overwrite the buffer
@@ -769,20 +855,25 @@ extern "C" int qj_program_create(qj_handle *h, int dtype, int nqubits, const qj_
         const int Tv = T - VS;
 
         // one launch = the rounds whose image fits the shared-memory budget
-        std::vector<Unit> round_units, outer_units, op_units;
+        std::vector<Unit> round_units, outer_units, op_units, h_units;
         int launch_rounds = 0, launch_ops = 0;
         auto close_launch = [&]() {
             if (launch_rounds == 0) return;
             std::vector<Unit> img;
-            Unit hdr;
-            const uint32_t off_rounds = 1, off_outer = off_rounds + uint32_t(round_units.size());
-            const uint32_t off_ops = off_outer + uint32_t(outer_units.size());
+            Unit hdr, hdr1;
+            memset(&hdr1, 0, sizeof(hdr1));
+            const uint32_t off_rounds = 2, off_outer = off_rounds + uint32_t(round_units.size());
+            const uint32_t off_h = off_outer + uint32_t(outer_units.size());
+            const uint32_t off_ops = off_h + uint32_t(h_units.size());
             hdr.w[0] = uint32_t(launch_rounds); hdr.w[1] = uint32_t(outer_units.size() / 2);
             hdr.w[2] = off_rounds; hdr.w[3] = off_outer;
+            hdr1.w[0] = uint32_t(h_units.size() / 4); hdr1.w[1] = off_h;
             img.push_back(hdr);
+            img.push_back(hdr1);
             for (size_t i = 0; i < round_units.size(); i += 3) round_units[i].w[0] += off_ops;   // first_unit
             img.insert(img.end(), round_units.begin(), round_units.end());
             img.insert(img.end(), outer_units.begin(), outer_units.end());
+            img.insert(img.end(), h_units.begin(), h_units.end());
             img.insert(img.end(), op_units.begin(), op_units.end());
             qj_program::Launch L;
             L.geom = geo;
@@ -790,10 +881,12 @@ extern "C" int qj_program_create(qj_handle *h, int dtype, int nqubits, const qj_
             L.blob_off = int64_t(blob_all.size());
             L.nrounds = launch_rounds;
             L.nops = launch_ops;
-            L.smem = (size_t(1) << Tv) * 16 + img.size() * 16 + (size_t(8) << geo.nh) + (outer_units.size() / 2) * 4 + 16;
+            L.geom.nH = int(h_units.size() / 4);
+            L.smem = (size_t(1) << Tv) * 16 + img.size() * 16 + (h_units.size() / 4) * 16 + (size_t(8) << geo.nh) +
+                     (outer_units.size() / 2) * 4 + 16;
             prog->launches.push_back(L);
             blob_all.insert(blob_all.end(), img.begin(), img.end());
-            round_units.clear(); outer_units.clear(); op_units.clear();
+            round_units.clear(); outer_units.clear(); op_units.clear(); h_units.clear();
             launch_rounds = 0; launch_ops = 0;
         };
 
@@ -886,8 +979,16 @@ extern "C" int qj_program_create(qj_handle *h, int dtype, int nqubits, const qj_
                 int oslot, nf;
                 uint32_t fields[9];
                 bool sign;
+                int cls;                 // 0: thread-only (folded into G), 1: outer-only (H), 2: mixed (per-thread look-up)
+                std::vector<cd> host;    // class 0: the slice's table, kept on the host
             };
             std::vector<PendingSlice> pending;
+            std::vector<Unit> r_H;          // per-tile factor entries of this round (4 units each)
+            const int h_base = int(h_units.size() / 4);
+            const int nthr_round = 1 << int(tq.size());
+            auto host_field = [](uint32_t base, uint32_t fl) -> uint32_t {
+                return ((base >> (fl & 255u)) & ((1u << ((fl >> 8) & 255u)) - 1u)) << (fl >> 16);
+            };
             std::vector<size_t> group_run;  // r_ops indices of the trailing run of plain one-target groups
             auto select_code = [&](uint32_t emask) -> uint32_t {
                 const uint32_t full = (N == 32) ? 0xffffffffu : 0xffffu;
@@ -910,14 +1011,57 @@ extern "C" int qj_program_create(qj_handle *h, int dtype, int nqubits, const qj_
                 std::vector<bool> done(pending.size(), false);
                 for (size_t i = 0; i < pending.size(); i++) {
                     if (done[i]) continue;
-                    std::vector<Unit> payload;
-                    int ntab = 0;
+                    std::vector<size_t> members;
                     bool allsign = true;
-                    for (size_t j = i; j < pending.size(); j++)
-                        if (!done[j] && pending[j].emask == pending[i].emask) allsign = allsign && pending[j].sign;
                     for (size_t j = i; j < pending.size(); j++) {
                         if (done[j] || pending[j].emask != pending[i].emask) continue;
                         done[j] = true;
+                        members.push_back(j);
+                        allsign = allsign && pending[j].sign;
+                    }
+                    // thread-only slices -> one factor per thread, computed here: a thread's tile
+                    // position (hence its index into each of these tables) is the same in every tile
+                    uint32_t g_off = 0xffffffffu;
+                    {
+                        std::vector<cd> G;
+                        for (size_t j : members) {
+                            const PendingSlice &ps = pending[j];
+                            if (ps.cls != 0) continue;
+                            if (G.empty()) G.assign(size_t(nthr_round), cd(1.0));
+                            for (int t = 0; t < nthr_round; t++) {
+                                uint32_t base = 0;
+                                for (size_t kb = 0; kb < tq.size(); kb++) if ((t >> kb) & 1) base |= 1u << (tq[kb] + VS);
+                                if ((base & ps.tmask) != ps.tmask) continue;
+                                uint32_t idx = 0;
+                                for (int f = 0; f < ps.nf; f++) idx |= host_field(base, ps.fields[f]);
+                                G[size_t(t)] *= ps.host[idx];
+                            }
+                        }
+                        if (!G.empty()) g_off = enc.push_table(G);
+                    }
+                    // outer-only slices -> one factor per tile (up to six look-ups per entry)
+                    uint32_t h_idx = 0xffffffffu;
+                    std::vector<size_t> cross;
+                    {
+                        std::vector<size_t> outer;
+                        for (size_t j : members) {
+                            if (pending[j].cls == 1 && outer.size() < 6) outer.push_back(j);
+                            else if (pending[j].cls != 0) cross.push_back(j);
+                        }
+                        if (!outer.empty()) {
+                            Unit u[4];
+                            memset(u, 0, sizeof(u));
+                            u[0].w[0] = uint32_t(outer.size());
+                            for (size_t t = 0; t < outer.size(); t++) {
+                                u[1 + t / 2].w[(t & 1) * 2] = pending[outer[t]].table;
+                                u[1 + t / 2].w[(t & 1) * 2 + 1] = uint32_t(pending[outer[t]].oslot);
+                            }
+                            h_idx = uint32_t(h_base) + uint32_t(r_H.size() / 4);
+                            for (int q = 0; q < 4; q++) r_H.push_back(u[q]);
+                        }
+                    }
+                    std::vector<Unit> payload;
+                    for (size_t j : cross) {
                         const PendingSlice &ps = pending[j];
                         Unit d0, d1, d2;
                         memset(&d1, 0, sizeof(d1)); memset(&d2, 0, sizeof(d2));
@@ -928,14 +1072,15 @@ extern "C" int qj_program_create(qj_handle *h, int dtype, int nqubits, const qj_
                         for (int f = 0; f < 4; f++) { d1.w[f] = ps.fields[1 + f]; d2.w[f] = ps.fields[5 + f]; }
                         payload.push_back(d0); payload.push_back(d1);
                         if (ps.nf > 5) payload.push_back(d2);
-                        ntab++;
                     }
                     Unit h0, h1;
                     memset(&h1, 0, sizeof(h1));
                     h0.w[0] = uint32_t(C_PHASE) | (uint32_t(2 + payload.size()) << 16);
-                    h0.w[1] = uint32_t(ntab) | (select_code(pending[i].emask) << 16);
+                    h0.w[1] = uint32_t(cross.size()) | (select_code(pending[i].emask) << 16);
                     h0.w[2] = allsign ? 1u : 0u;
                     h0.w[3] = pending[i].emask;
+                    h1.w[0] = g_off;
+                    h1.w[1] = h_idx;
                     r_ops.push_back(h0); r_ops.push_back(h1);
                     r_ops.insert(r_ops.end(), payload.begin(), payload.end());
                     r_nops++;
@@ -1133,11 +1278,17 @@ extern "C" int qj_program_create(qj_handle *h, int dtype, int nqubits, const qj_
                             }
                             if (emask == 0) continue;
                             PendingSlice ps;
-                            memset(&ps, 0, sizeof(ps));
                             ps.emask = emask; ps.tmask = tmask; ps.oslot = oslot; ps.nf = nf;
-                            for (int f = 0; f < nf; f++) ps.fields[f] = fields[f];
+                            for (int f = 0; f < 9; f++) ps.fields[f] = (f < nf) ? fields[f] : 0u;
                             ps.sign = sl.sign;
-                            ps.table = enc.push_table(sl.t);   // a constant phase is a one-entry table
+                            ps.table = 0;
+                            if (oslot == 0xffff) {                 // no outer bits, no outer controls
+                                ps.cls = 0;
+                                ps.host = sl.t;
+                            } else {
+                                ps.cls = (nf == 0 && tmask == 0) ? 1 : 2;
+                                ps.table = enc.push_table(sl.t);
+                            }
                             pending.push_back(ps);
                         }
                     } else {
@@ -1165,17 +1316,36 @@ extern "C" int qj_program_create(qj_handle *h, int dtype, int nqubits, const qj_
 
             flush_pending();
 
+            // prefetch links: every op names the per-thread factor table of the next phase group
+            uint32_t first_g = 0xffffffffu;
+            {
+                std::vector<size_t> starts;
+                for (size_t i = 0; i < r_ops.size(); i += r_ops[i].w[0] >> 16) starts.push_back(i);
+                uint32_t next_g = 0xffffffffu;
+                for (size_t k = starts.size(); k-- > 0;) {
+                    const size_t i = starts[k];
+                    const uint32_t code = r_ops[i].w[0] & 0xffffu;
+                    if (code != uint32_t(C_DIAGN)) r_ops[i + 1].w[2] = next_g;
+                    if (code == uint32_t(C_PHASE) && r_ops[i + 1].w[0] != 0xffffffffu) next_g = r_ops[i + 1].w[0];
+                }
+                first_g = next_g;
+            }
+
             // append the round (closing the launch first when the image would overflow)
-            const size_t need_units = 1 + round_units.size() + 3 + outer_units.size() + r_outer.size() + op_units.size() + r_ops.size();
-            if (3 + r_outer.size() + r_ops.size() + 1 > size_t(kMaxBlobUnits) || r_outer.size() / 2 > size_t(kMaxOuter))
+            const size_t need_units = 2 + round_units.size() + 3 + outer_units.size() + r_outer.size() + h_units.size() +
+                                      r_H.size() + op_units.size() + r_ops.size() + (h_units.size() + r_H.size()) / 4;
+            if (3 + r_outer.size() + r_ops.size() + r_H.size() + r_H.size() / 4 + 2 > size_t(kMaxBlobUnits) ||
+                r_outer.size() / 2 > size_t(kMaxOuter))
                 return bail("round: too many ops for one round");
             if (need_units > size_t(kMaxBlobUnits) || (outer_units.size() + r_outer.size()) / 2 > size_t(kMaxOuter)) {
-                // the outer slots of this round were numbered relative to the open launch: renumber
+                // the outer slots / factor indices of this round were numbered relative to the open
+                // launch: renumber
                 close_launch();
                 for (size_t i = 0; i < r_ops.size();) {
                     const uint32_t units = r_ops[i].w[0] >> 16;
                     if ((r_ops[i].w[0] & 0xffffu) == uint32_t(C_PHASE)) {  // slots live in the table descriptors
                         const int ntab = int(r_ops[i].w[1] & 0xffffu);
+                        if (r_ops[i + 1].w[1] != 0xffffffffu) r_ops[i + 1].w[1] -= uint32_t(h_base);
                         size_t d = i + 2;
                         for (int t = 0; t < ntab; t++) {
                             const uint32_t nf = r_ops[d].w[1] & 0xffffu, oslot = r_ops[d].w[1] >> 16;
@@ -1187,6 +1357,10 @@ extern "C" int qj_program_create(qj_handle *h, int dtype, int nqubits, const qj_
                         if (oslot != 0xffffu) r_ops[i].w[1] = (r_ops[i].w[1] & 0xffff0000u) | (oslot - uint32_t(outer_base));
                     }
                     i += units;
+                }
+                for (size_t e = 0; e < r_H.size(); e += 4) {
+                    const uint32_t ntab = r_H[e].w[0];
+                    for (uint32_t t = 0; t < ntab; t++) r_H[e + 1 + t / 2].w[(t & 1) * 2 + 1] -= uint32_t(outer_base);
                 }
             }
             if (r_nops > 0) {
@@ -1200,8 +1374,10 @@ extern "C" int qj_program_create(qj_handle *h, int dtype, int nqubits, const qj_
                     u1.w[kbit >> 1] |= td << ((kbit & 1) * 16);
                     u2.w[kbit >> 2] |= uint32_t(tq[kbit] + VS) << ((kbit & 3) * 8);
                 }
+                u2.w[2] = first_g;
                 round_units.push_back(u0); round_units.push_back(u1); round_units.push_back(u2);
                 outer_units.insert(outer_units.end(), r_outer.begin(), r_outer.end());
+                h_units.insert(h_units.end(), r_H.begin(), r_H.end());
                 op_units.insert(op_units.end(), r_ops.begin(), r_ops.end());
                 launch_rounds++;
                 launch_ops += r_nops;

@@ -127,6 +127,13 @@ class LocalSegment:
         self.compiled = None
 
 
+class Plan(list):
+    """[LocalSegment | Exchange] steps of one gate list + the qubit maps before and after it."""
+
+    initial_map = None
+    final_map = None
+
+
 class Exchange:
     """Swap rank bit `rank_bit` with shard index bit `local_bit` (half a shard each way)."""
 
@@ -153,6 +160,7 @@ class DistributedState:
         self.swap_chunk_bytes = swap_chunk_bytes
         self.stats = {"exchanges": 0, "exchange_bytes": 0, "local_gates": 0, "local_segments": 0,
                       "skipped": 0, "relabelled_swaps": 0}
+        self._fresh = True   # still |0...0>: the qubit map may be chosen freely
         self.shard = backend.shard_zeros(self.nlocal, self.dtype, one_at_zero=(self.rank == 0))
 
     # ------------------------------------------------------------------ helpers
@@ -306,28 +314,146 @@ class DistributedState:
         else:
             self._emit_phase(plan, complex(d[0]), lcontrols)
 
-    def plan(self, queue):
+    def plan(self, queue, reorder=True, free_initial_map=None):
         """Gate list -> [LocalSegment | Exchange] for this rank, advancing the qubit map.  The
-        exchange steps are identical on every rank (victims depend on the map and on a look-ahead
-        over the list only); the local gates differ by the rank predicates."""
-        needs = [self._needs_local(g, self.backend.custom_matrices) for g in queue]
-        # table[i][q] = index of the next gate after i that needs q local
-        nxt = {}
-        table = [None] * len(queue)
-        for i in range(len(queue) - 1, -1, -1):
-            table[i] = dict(nxt)
+        exchange steps are identical on every rank (they depend on the map and the gate list
+        only); the local gates differ by the rank predicates.
+
+        With `reorder` the list is treated as its dependency DAG (gates sharing a qubit keep their
+        order): every ready gate whose non-diagonal targets are local runs first, and an exchange
+        happens only when nothing else can run.  The evicted local qubit is the one with the
+        fewest remaining gates that need it local (a finished qubit costs no later exchange),
+        ties broken by the farthest next use.  `reorder=False` keeps program order with a
+        look-ahead victim choice.
+
+        `free_initial_map` (default: True while the state is still |0...0>, which is symmetric
+        under qubit relabelling): the qubits whose first non-diagonal gate comes latest start as
+        the global ones, at no cost."""
+        gates = []
+        for g in queue:
+            if getattr(g, "name", "") == "fanout":
+                from . import gates as G
+
+                gates.extend(G.CNOT(g.control_qubits[0], t) for t in g.target_qubits)
+            else:
+                gates.append(g)
+        needs = [self._needs_local(g, self.backend.custom_matrices) for g in gates]
+        if free_initial_map is None:
+            free_initial_map = self._fresh and reorder
+        if free_initial_map and self.nglobal:
+            if not self._fresh:
+                raise ValueError("the initial qubit map is only free for the |0...0> state")
+            first = {}
+            for i, nd in enumerate(needs):
+                for q in nd:
+                    first.setdefault(q, i)
+            order = sorted(range(self.nqubits), key=lambda q: (-first.get(q, len(gates)), -q))
+            glob = sorted(order[:self.nglobal])
+            loc = [q for q in range(self.nqubits) if q not in glob]
+            for k, q in enumerate(glob):
+                self.bit_of[q] = self.nqubits - 1 - k
+            for k, q in enumerate(loc):
+                self.bit_of[q] = self.nlocal - 1 - k
+        self._fresh = False
+        steps = Plan()
+        steps.initial_map = list(self.bit_of)
+        if not reorder:
+            # table[i][q] = index of the next gate after i that needs q local
+            nxt = {}
+            table = [None] * len(gates)
+            for i in range(len(gates) - 1, -1, -1):
+                table[i] = dict(nxt)
+                for q in needs[i]:
+                    nxt[q] = i
+            for i, gate in enumerate(gates):
+                look = {q: (j - i) for q, j in table[i].items()}
+                self._plan_gate(steps, gate, look)
+            steps.final_map = list(self.bit_of)
+            return steps
+
+        # dependency DAG by shared qubits
+        npred = [0] * len(gates)
+        succ = [[] for _ in gates]
+        last = {}
+        for i, g in enumerate(gates):
+            for q in set(g.qubits):
+                j = last.get(q)
+                if j is not None and i not in succ[j]:
+                    succ[j].append(i)
+                    npred[i] += 1
+                last[q] = i
+        uses = {q: [] for q in range(self.nqubits)}     # indices of the gates that need q local
+        for i, nd in enumerate(needs):
+            for q in nd:
+                uses[q].append(i)
+        upos = {q: 0 for q in uses}                      # first not-yet-run entry of uses[q]
+        done = [False] * len(gates)
+        import heapq
+
+        ready = [i for i in range(len(gates)) if npred[i] == 0]
+        heapq.heapify(ready)
+        blocked = []
+        ndone = 0
+        while ndone < len(gates):
+            progressed = False
+            while ready:
+                i = heapq.heappop(ready)
+                if all(self.is_local(q) for q in needs[i]):
+                    self._plan_gate(steps, gates[i], None)
+                    done[i] = True
+                    ndone += 1
+                    progressed = True
+                    for j in succ[i]:
+                        npred[j] -= 1
+                        if npred[j] == 0:
+                            heapq.heappush(ready, j)
+                    if blocked and GATE_OPS.get(gates[i].__class__.__name__) == "apply_swap":
+                        for j in blocked:               # a relabelling SWAP may have unblocked them
+                            heapq.heappush(ready, j)
+                        blocked = []
+                else:
+                    blocked.append(i)
+            if ndone == len(gates):
+                break
+            # nothing can run: bring in the qubits of the earliest blocked gate
+            assert blocked, "dependency cycle in the gate list"
+            i = min(blocked)
+            for q in uses:
+                while upos[q] < len(uses[q]) and done[uses[q][upos[q]]]:
+                    upos[q] += 1
             for q in needs[i]:
-                nxt[q] = i
-        steps = []
-        for i, gate in enumerate(queue):
-            look = {q: (j - i) for q, j in table[i].items()}
-            self._plan_gate(steps, gate, look)
+                if self.is_local(q):
+                    continue
+                best, best_key = None, None
+                for v in range(self.nqubits):
+                    if not self.is_local(v) or v in needs[i]:
+                        continue
+                    if self.dtype == "complex64" and self.bit_of[v] == 0:
+                        continue  # 16-byte exchange granularity
+                    left = len(uses[v]) - upos[v]
+                    nxt_use = uses[v][upos[v]] if left else len(gates)
+                    key = (left, -nxt_use, -self.bit_of[v])   # prefer the top bit: contiguous halves
+                    if best is None or key < best_key:
+                        best, best_key = v, key
+                if best is None:
+                    raise RuntimeError("no local qubit available to swap with")
+                self._plan_exchange(steps, q, best)
+            for j in blocked:
+                heapq.heappush(ready, j)
+            blocked = []
+        steps.final_map = list(self.bit_of)
         return steps
 
     def run(self, steps):
         """Execute planned steps on the shard (local segments are compiled into multi-gate pass
         programs by the backend the first time they run, and cached on the step)."""
         b = self.backend
+        initial = getattr(steps, "initial_map", None)
+        if initial is not None and list(initial) != self.bit_of and getattr(steps, "final_map", None) != self.bit_of:
+            # (a plan made on this state has already advanced the map to its final_map)
+            if not self._fresh:
+                raise ValueError("plan was made for a different qubit map")
+        self._fresh = False
         for step in steps:
             if isinstance(step, LocalSegment):
                 self.shard = b.run_local_segment(self.shard, self.nlocal, step)
@@ -338,6 +464,8 @@ class DistributedState:
                                          (self.rank >> step.rank_bit) & 1, self.comm, self.swap_chunk_bytes)
                 self.stats["exchanges"] += 1
                 self.stats["exchange_bytes"] += int(moved)
+        if getattr(steps, "final_map", None) is not None:
+            self.bit_of = list(steps.final_map)
         return self
 
     def apply_gate(self, gate, lookahead=None):
@@ -370,6 +498,7 @@ class DistributedState:
         """Back to |0...0> with the identity qubit map (in place)."""
         self.backend.shard_reset(self.shard, self.nlocal, one_at_zero=(self.rank == 0))
         self.bit_of = [self.nqubits - 1 - q for q in range(self.nqubits)]
+        self._fresh = True
         return self
 
     # ------------------------------------------------------------------ results
@@ -410,12 +539,8 @@ def execute_distributed_circuit(backend, circuit, initial_state=None, nshots=Non
     state = DistributedState(backend, circuit.nqubits, comm=comm)
     key = ("dist", state.rank, state.comm.world, backend.dtype)
     cache = circuit.__dict__.setdefault("_qj_programs", {})
-    if key in cache:
-        steps, final_map = cache[key]
-        state.run(steps)
-        state.bit_of = list(final_map)
-    else:
-        steps = state.plan(circuit.queue)
-        state.run(steps)
-        cache[key] = (steps, list(state.bit_of))
+    steps = cache.get(key)
+    if steps is None:
+        steps = cache[key] = state.plan(circuit.queue)
+    state.run(steps)
     return state

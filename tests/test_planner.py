@@ -79,7 +79,7 @@ def test_qft_plan_small_matches_analytic():
 
 
 def test_diagonal_controls_are_split_off():
-    n = 8
+    n = 10   # all four qubits lie outside the 6-bit tile: one table family
     glist = [gates.CU1(1, 0, 0.3), gates.CU1(2, 0, 0.5), gates.CU1(3, 0, 0.7)]
     plan = planner.plan_queue(glist, n, MATS, 6, 3)
     assert len(plan) == 1 and len(_ops(plan)) == 1
@@ -95,3 +95,18 @@ def test_rounds_hoist_commuting_gates():
     assert len(plan) == 1 and len(plan[0][2]) == 3      # 12 H gates, 4 register bits per round
     plan64 = planner.plan_queue(glist, n, MATS, 12, 5, dtype="complex64")
     assert len(plan64[0][2]) == 3 and all(0 in regs for regs, _ in plan64[0][2])
+
+
+def test_phase_tables_are_split_by_locality():
+    """Within a round, tables over tile-local bits, over outer bits and over both are kept apart
+    (the kernel turns the first two kinds into one factor per thread / per tile)."""
+    n = 16
+    plan = planner.plan_queue(circuits.qft(n).queue, n, MATS, 8, 3)
+    for seg in plan:
+        local = set(seg[1])
+        for regs, ops in seg[2]:
+            for op in ops:
+                if op.kind != "diag":
+                    continue
+                rest = op.bits - set(regs)
+                assert rest <= local or not (rest & local), (sorted(rest), sorted(local))

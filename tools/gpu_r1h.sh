@@ -2,7 +2,7 @@
 # pass kernel v4 (uniform op loop, one-target group ops, runtime CTA size): parity, timing, ncu
 set -x
 mkdir -p gpurun_out
-TAG=${TAG:-r1h}
+TAG=${TAG:-r1m}
 timeout 1200 python -m pytest tests/test_program_gpu.py -x -q 2>&1 | tail -5
 for args in "--workload variational --nqubits 30" "--workload variational --nqubits 30 --tile-bits 11" \
             "--workload qft --nqubits 30" "--workload qft --nqubits 30 --tile-bits 11" "--workload qft --nqubits 33" \
