@@ -220,6 +220,45 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------- GPU arm
+def measurement_leg(backend, state, nqubits, dtype, nshots=10 ** 6):
+    """BASELINE.json configs[4]: full-register probabilities, 10^6-shot sampling (the reference's
+    Metropolis sampler semantics, ops.py:86-108) and one collapse on three qubits, timed once each
+    with CUDA events on the launch stream.  Checked: the shot counts add up, the collapsed state is
+    normalised."""
+    import torch
+
+    def timed(fn):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        out = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return out, e0.elapsed_time(e1)
+
+    amp = 16 if dtype == "complex128" else 8
+    np.random.seed(123)
+    probs, ms_probs = timed(lambda: backend.calculate_probabilities(state, list(range(nqubits)), nqubits))
+    freqs, ms_sample = timed(lambda: backend.sample_frequencies(probs, nshots))
+    assert sum(freqs.values()) == nshots, sum(freqs.values())
+    del probs
+    torch.cuda.empty_cache()
+    shot = max(freqs, key=freqs.get)
+    qubits = [1, nqubits // 2, nqubits - 2]
+    outcome = sum(((shot >> (nqubits - 1 - q)) & 1) << (len(qubits) - 1 - i) for i, q in enumerate(qubits))
+    _, ms_collapse = timed(lambda: backend.collapse_state(state, qubits, outcome, nqubits))
+    norm = backend.calculate_norm(state)
+    assert abs(norm - 1.0) < (1e-9 if dtype == "complex128" else 1e-4), norm
+    nbytes = amp << nqubits
+    return {"nshots": nshots, "distinct_outcomes": len(freqs),
+            "probabilities_ms": ms_probs, "probabilities_gbs": nbytes / (ms_probs * 1e-3) / 1e9,
+            "sample_frequencies_ms": ms_sample, "shots_per_second": nshots / (ms_sample * 1e-3),
+            "collapse_qubits": qubits, "collapse_ms": ms_collapse,
+            # zero 7/8 of the state, read 1/8 for the norm, rescale 1/8 (SURVEY.md 8d)
+            "collapse_gbs": nbytes * (7 / 8 + 1 / 8 + 2 / 8) / (ms_collapse * 1e-3) / 1e9,
+            "norm_after_collapse": norm}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -309,6 +348,26 @@ def run_ours(args):
     breakdown = {k: {"launches_per_step": v["n"] // args.steps, "avg_ms": v["ms"] / v["n"],
                      "gbs": v["bytes"] / (v["ms"] * 1e-3) / 1e9} for k, v in per_kind.items()}
     kernel_names = {"pass": "k_pass (multi-gate tile pass, 2*N*A bytes per launch)"}
+    # arithmetic side: a pass that absorbs many dense gates is bound by the FP64 / FP32 pipe, not by HBM
+    fma = prog.fma_per_amplitude()
+    pass_ms = per_kind.get("pass", {"ms": 0.0})["ms"] / args.steps
+    fp_peak = 37.2 if dtype == "complex128" else 74.5   # nominal CUDA-core peaks: 148 SMs x 64 (128) lanes x 2 x 1.965 GHz
+    fp = {"fma_per_amplitude_per_step": fma, "tflops": 2.0 * fma * 2.0 ** nqubits / (pass_ms * 1e-3) / 1e12 if pass_ms else None,
+          "peak_tflops_nominal": fp_peak, "pipe": "fp64" if dtype == "complex128" else "fp32",
+          "hbm_bound_ms": pstats["launches"] * 2.0 * nbytes_state / (peak * 1e9) * 1e3,
+          "fp_bound_ms": 2.0 * fma * 2.0 ** nqubits / (fp_peak * 1e12) * 1e3}
+    traffic, traffic_src = None, None
+    prof = os.path.join(ROOT, "profiles", "r1o_ncu_pass_var30_full_summary.csv")
+    if args.workload == "variational" and nqubits == 30 and dtype == "complex128" and os.path.exists(prof):
+        import csv
+
+        vals = {r[0]: r[2] for r in csv.reader(open(prof)) if len(r) == 3}
+        traffic = (float(vals["dram__bytes_read.sum"]) + float(vals["dram__bytes_write.sum"])) * 1e9
+        traffic_src = "profiles/r1o_ncu_pass_var30_full_summary.csv (ncu --set full, first k_pass launch of this workload)"
+
+    measurement = None
+    if args.workload == "qv" or args.measure:
+        measurement = measurement_leg(backend, state, nqubits, dtype)
 
     # end to end through the public API, every step from HOST gate objects: plan + encode the
     # passes, upload the program image and phase tables, run, read a marginal back
@@ -349,8 +408,9 @@ def run_ours(args):
                    "l2_policy": "state (>= 16 GiB) is far larger than the 126 MB L2; no flush needed",
                    "timing": "CUDA events on the launch stream"},
         "roofline": {"bound": "hbm", "kernel": kernel_names.get(dom, dom), "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                     "per_kernel": breakdown},
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                     "algorithmic_bytes_per_launch": 2.0 * nbytes_state, "peak_source": peak_src,
+                     "per_kernel": breakdown, "arithmetic": fp},
         "cpu_baseline": {"value": cpu_gps, "unit": "gates/s", "cores": cores, "kind": "port", "sample": cpu_desc},
         "e2e": {"value": e2e_value, "unit": "gates/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h),
@@ -358,6 +418,8 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "clocks": clocks.summary(),
     }
+    if measurement is not None:
+        line["measurement"] = measurement
     print(json.dumps(line))
 
 
@@ -372,6 +434,8 @@ def main():
     ap.add_argument("--fuse", type=int, default=0)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--measure", action="store_true",
+                    help="append the measurement leg (probabilities, 10^6 shots, collapse); default for --workload qv")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

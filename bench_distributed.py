@@ -135,7 +135,7 @@ def run_distributed(args, backend, nqubits, dtype, fuse, world, rank):
     from qibojit_b200.distributed import LocalSegment
 
     h2d = sum(st.compiled.upload_bytes for st in steps if isinstance(st, LocalSegment) and st.compiled is not None)
-    assert abs(host.sum() - 1.0) < 1e-5, host.sum()
+    assert abs(host.sum() - 1.0) < (1e-6 if dtype == "complex128" else 1e-3), host.sum()
 
     if rank == 0:
         line = {

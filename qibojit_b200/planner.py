@@ -444,6 +444,32 @@ class Program:
                 state = out[0]
         return state
 
+    def fma_per_amplitude(self):
+        """Real multiply-adds per amplitude the pass kernel executes for this program (the
+        arithmetic side of the roofline): 4 for a real or axis-aligned one-target gate, 8 for a
+        complex one, 16 for a two-target gate, 4 per phase multiply; permutations and sign flips
+        cost none; controls scale by 2^-c."""
+        total = 0.0
+        for _, rounds in self.passes:
+            for _, ops in rounds:
+                for op in ops:
+                    frac = 2.0 ** -len(op.controls)
+                    d = np.asarray(op.data)
+                    if op.kind == "dense" and len(op.targets) == 1:
+                        m = d.reshape(2, 2)
+                        if np.array_equal(m, [[0, 1], [1, 0]]):
+                            continue
+                        real = not np.any(m.imag)
+                        axis = not (m[0, 0].imag or m[1, 1].imag or m[0, 1].real or m[1, 0].real)
+                        total += (4.0 if (real or axis) else 8.0) * frac
+                    elif op.kind == "dense":
+                        total += 16.0 * frac
+                    elif op.kind == "diag":
+                        if np.all((d.imag == 0) & (np.abs(d.real) == 1)):
+                            continue
+                        total += 4.0 * frac * float(np.mean(d != 1.0))
+        return total
+
     def stats(self):
         """{'launches', 'rounds', 'micro_ops', 'raw_gates'} summed over the segments."""
         out = dict(launches=0, rounds=0, micro_ops=0, raw_gates=0, passes=len(self.passes))
