@@ -140,11 +140,68 @@ __device__ __forceinline__ void load_units(const uint4 *p, float (&d)[4 * NU]) {
 }
 
 // ---- ops on the register amplitudes ---------------------------------------------------------------
+// ---- packed FP32x2 arithmetic (sm_100a FFMA2 / FMUL2): a complex64 amplitude is one 64-bit
+// operand.  ptxas folds the packing below into operand modifiers (scalar broadcast, swapped
+// halves, per-half negation), so a complex multiply-accumulate is two instructions, no moves.
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 f2_fma(u64 a, u64 b, u64 c) {
+    u64 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ u64 f2_mul(u64 a, u64 b) {
+    u64 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ u64 f2_pack(float lo, float hi) {
+    u64 d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+    return d;
+}
+__device__ __forceinline__ u64 f2_of(const Cx<float> &c) { return f2_pack(c.re, c.im); }
+__device__ __forceinline__ u64 f2_swapped(const Cx<float> &c) { return f2_pack(c.im, c.re); }
+__device__ __forceinline__ u64 f2_splat(float v) { return f2_pack(v, v); }
+// a pair that must be built once and kept (not rematerialised at every use)
+__device__ __forceinline__ u64 f2_pack_once(float lo, float hi) {
+    u64 d;
+    asm volatile("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+    return d;
+}
+__device__ __forceinline__ void f2_store(Cx<float> &c, u64 v) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(c.re), "=f"(c.im) : "l"(v));
+}
+// A complex64 matrix element g travels as the two pairs S = (gr, gr), N = (-gi, gi) (complex64
+// payloads store them ready-made, 16 bytes per element): g * s = S * s + N * swapped(s).
+__device__ __forceinline__ u64 f2_cmac(u64 acc, u64 S, u64 Nn, const Cx<float> &s) {
+    acc = f2_fma(S, f2_of(s), acc);
+    return f2_fma(Nn, f2_swapped(s), acc);
+}
+__device__ __forceinline__ u64 f2_cmul(u64 S, u64 Nn, const Cx<float> &s) {
+    return f2_fma(Nn, f2_swapped(s), f2_mul(S, f2_of(s)));
+}
+
 // one-target gate on register slot A.  KIND 0: complex 2x2 (8 scalars), 1: real (4 scalars),
 // 2: real diagonal + imaginary off-diagonal, payload {g00, Im g01, Im g10, g11}.
 // The unmasked path (no register-slot controls) is straight-line code updating x in place.
 template <typename T, int A, int KIND>
 __device__ __forceinline__ void dense1_pair(Cx<T> &s0, Cx<T> &s1, const T *m) {
+    if constexpr (sizeof(T) == 4) {
+        u64 y0, y1;
+        if (KIND == 1) {
+            y0 = f2_fma(f2_splat(m[0]), f2_of(s0), f2_mul(f2_splat(m[1]), f2_of(s1)));
+            y1 = f2_fma(f2_splat(m[3]), f2_of(s1), f2_mul(f2_splat(m[2]), f2_of(s0)));
+        } else if (KIND == 2) {   // payload {a, d, -b, b, -c, c, 0, 0}: i b s = (-b, b) * swapped(s)
+            y0 = f2_fma(f2_splat(m[0]), f2_of(s0), f2_mul(f2_pack(m[2], m[3]), f2_swapped(s1)));
+            y1 = f2_fma(f2_splat(m[1]), f2_of(s1), f2_mul(f2_pack(m[4], m[5]), f2_swapped(s0)));
+        } else {                  // payload {gr, gr, -gi, gi} per element
+            y0 = f2_cmac(f2_cmul(f2_pack(m[0], m[1]), f2_pack(m[2], m[3]), s0), f2_pack(m[4], m[5]), f2_pack(m[6], m[7]), s1);
+            y1 = f2_cmac(f2_cmul(f2_pack(m[8], m[9]), f2_pack(m[10], m[11]), s0), f2_pack(m[12], m[13]), f2_pack(m[14], m[15]), s1);
+        }
+        f2_store(s0, y0);
+        f2_store(s1, y1);
+        return;
+    }
     if (KIND == 1) {
         const T t0 = m[1] * s1.re, t1 = m[1] * s1.im, u0 = m[2] * s0.re, u1 = m[2] * s0.im;
         s0.re = fma(m[0], s0.re, t0); s0.im = fma(m[0], s0.im, t1);
@@ -168,7 +225,8 @@ template <typename T, int A, int KIND>
 __device__ __forceinline__ void op_dense1(Cx<T> (&x)[Lay<T>::N], const uint4 *pay, uint32_t emask) {
     constexpr int N = Lay<T>::N;
     if constexpr (A < Lay<T>::J) {
-        constexpr int NS = (KIND == 0) ? 8 : 4;          // scalars in the payload (a whole number of units)
+        // scalars in the payload (a whole number of units); complex64 complex elements are 4 floats
+        constexpr int NS = (sizeof(T) == 4) ? (KIND == 0 ? 16 : KIND == 2 ? 8 : 4) : (KIND == 0 ? 8 : 4);
         T m[NS];
         load_units<NS * sizeof(T) / 16>(pay, m);
         if (emask == (N == 32 ? 0xffffffffu : 0xffffu)) {
@@ -190,7 +248,7 @@ __device__ __forceinline__ void op_dense1(Cx<T> (&x)[Lay<T>::N], const uint4 *pa
 
 template <typename T, int KIND>
 __device__ __forceinline__ void op_group1(Cx<T> (&x)[Lay<T>::N], const uint4 *pay, uint32_t slots, uint32_t emask) {
-    constexpr int NU = ((KIND == 0) ? 8 : 4) * sizeof(T) / 16;   // units per matrix
+    constexpr int NU = (sizeof(T) == 4) ? (KIND == 0 ? 4 : KIND == 2 ? 2 : 1) : (KIND == 0 ? 4 : 2);   // units per matrix
     if (slots & 1u) { op_dense1<T, 0, KIND>(x, pay, emask); pay += NU; }
     if (slots & 2u) { op_dense1<T, 1, KIND>(x, pay, emask); pay += NU; }
     if (slots & 4u) { op_dense1<T, 2, KIND>(x, pay, emask); pay += NU; }
@@ -205,6 +263,21 @@ __device__ __forceinline__ void dense2_group(Cx<T> (&x)[Lay<T>::N], const uint4 
     Cx<T> s[4], y[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) s[j] = x[e0 | ((j & 1) << A) | ((j >> 1) << B)];
+    if constexpr (sizeof(T) == 4) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            float g[16];                                  // row i: {gr, gr, -gi, gi} x 4
+            load_units<4>(pay + i * 4, g);
+            u64 acc = f2_cmul(f2_pack(g[0], g[1]), f2_pack(g[2], g[3]), s[0]);
+#pragma unroll
+            for (int j = 1; j < 4; j++)
+                acc = f2_cmac(acc, f2_pack(g[4 * j], g[4 * j + 1]), f2_pack(g[4 * j + 2], g[4 * j + 3]), s[j]);
+            f2_store(y[i], acc);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) x[e0 | ((i & 1) << A) | ((i >> 1) << B)] = y[i];
+        return;
+    }
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         T g[8];
@@ -266,6 +339,10 @@ __device__ __forceinline__ void op_perm2(Cx<T> (&x)[Lay<T>::N], uint32_t emask) 
 
 template <typename T>
 __device__ __forceinline__ void cmul_inplace(Cx<T> &v, T pr, T pi) {
+    if constexpr (sizeof(T) == 4) {
+        f2_store(v, f2_cmul(f2_splat(pr), f2_pack(-pi, pi), v));
+        return;
+    }
     const T t = pi * v.im, u = pi * v.re;
     v.re = fma(pr, v.re, -t);
     v.im = fma(pr, v.im, u);
@@ -300,11 +377,20 @@ __device__ __forceinline__ void flip_masked(Cx<T> (&x)[Lay<T>::N], uint32_t emas
 template <typename T, int BITS, bool SIGN>
 __device__ __forceinline__ void phase_static(Cx<T> (&x)[Lay<T>::N], T pr, T pi, uint32_t sg) {
     if constexpr (BITS < Lay<T>::N) {
+        if constexpr (sizeof(T) == 4 && !SIGN) {
+            const u64 S = f2_pack_once(pr, pr), Nn = f2_pack_once(-pi, pi);
 #pragma unroll
-        for (int e = 0; e < Lay<T>::N; e++) {
-            if ((e & BITS) != BITS) continue;
-            if (SIGN) { x[e].re = flip(x[e].re, sg); x[e].im = flip(x[e].im, sg); }
-            else cmul_inplace<T>(x[e], pr, pi);
+            for (int e = 0; e < Lay<T>::N; e++) {
+                if ((e & BITS) != BITS) continue;
+                f2_store(x[e], f2_cmul(S, Nn, x[e]));
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < Lay<T>::N; e++) {
+                if ((e & BITS) != BITS) continue;
+                if (SIGN) { x[e].re = flip(x[e].re, sg); x[e].im = flip(x[e].im, sg); }
+                else cmul_inplace<T>(x[e], pr, pi);
+            }
         }
     }
 }
@@ -751,6 +837,19 @@ struct Encoder {
         }
         return off;
     }
+    // complex matrix elements: complex128 (re, im); complex64 the ready-made FP32x2 operand pairs
+    // (re, re, -im, im), 16 bytes per element either way
+    void push_complex(std::vector<Unit> &out, const std::vector<cd> &z) const {
+        std::vector<double> sc;
+        for (const cd &g : z) {
+            if (dtype == QJ_C128) {
+                sc.push_back(g.real()); sc.push_back(g.imag());
+            } else {
+                sc.push_back(g.real()); sc.push_back(g.real()); sc.push_back(-g.imag()); sc.push_back(g.imag());
+            }
+        }
+        push_scalars(out, sc);
+    }
     // scalars (state precision) appended to a unit stream
     void push_scalars(std::vector<Unit> &out, const std::vector<double> &s) const {
         std::vector<unsigned char> raw;
@@ -1141,12 +1240,14 @@ extern "C" int qj_program_create(qj_handle *h, int dtype, int nqubits, const qj_
                                 enc.push_scalars(payload, {m[0].real(), m[1].real(), m[2].real(), m[3].real()});
                             } else if (m[0].imag() == 0.0 && m[3].imag() == 0.0 && m[1].real() == 0.0 && m[2].real() == 0.0) {
                                 code = C_GROUP1X;
-                                enc.push_scalars(payload, {m[0].real(), m[1].imag(), m[2].imag(), m[3].real()});
+                                if (dtype == QJ_C128)
+                                    enc.push_scalars(payload, {m[0].real(), m[1].imag(), m[2].imag(), m[3].real()});
+                                else   // packed FP32x2: {a, d, -b, b, -c, c, 0, 0}
+                                    enc.push_scalars(payload, {m[0].real(), m[3].real(), -m[1].imag(), m[1].imag(),
+                                                               -m[2].imag(), m[2].imag(), 0.0, 0.0});
                             } else {
                                 code = C_GROUP1C;
-                                std::vector<double> sc;
-                                for (const cd &z : m) { sc.push_back(z.real()); sc.push_back(z.imag()); }
-                                enc.push_scalars(payload, sc);
+                                enc.push_complex(payload, m);
                             }
                             const uint32_t full = (N == 32) ? 0xffffffffu : 0xffffu;
                             const bool plain = cmask_e == full && tmask == 0 && oslot == 0xffff;
@@ -1195,9 +1296,7 @@ extern "C" int qj_program_create(qj_handle *h, int dtype, int nqubits, const qj_
                         if (is_swap) {
                             push_op(C_PERM2 + pair_index(a, b), oslot, 0, tmask, cmask_e, 0, nullptr, payload);
                         } else {
-                            std::vector<double> s;
-                            for (const cd &z : m) { s.push_back(z.real()); s.push_back(z.imag()); }
-                            enc.push_scalars(payload, s);
+                            enc.push_complex(payload, m);
                             push_op(C_DENSE2 + pair_index(a, b), oslot, 0, tmask, cmask_e, 0, nullptr, payload);
                         }
                     }
