@@ -12,7 +12,7 @@ SOURCES = ["capi.cu", "gate_kernels.cu", "tile_kernels.cu", "ops_kernels.cu", "p
 HEADERS = ["common.cuh", os.path.join("..", "..", "include", "qibojit_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "128",
 ]
 
 

@@ -438,7 +438,6 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
                  "l"(gmem_src)
                  : "memory");
 }
-__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // tile constant of outer slot m: -1 when its outer controls are not satisfied by this tile, else
@@ -567,7 +566,6 @@ k_pass(Cx<T> *__restrict__ state, const __grid_constant__ PassGeom pg, const uin
 #pragma unroll 1
         for (int rd = 0; rd < nrounds; rd++) {
             const uint4 r0 = rounds[3 * rd], r1 = rounds[3 * rd + 1], r2 = rounds[3 * rd + 2];
-            if (r2.z != 0xffffffffu) prefetch_l1(tables + r2.z + tid);         // G of the round's first phase group
             {
                 uint32_t vd[4] = {r0.z & 0xffffu, r0.z >> 16, r0.w & 0xffffu, r0.w >> 16};
                 const uint32_t tdw[4] = {r1.x, r1.y, r1.z, r1.w};
@@ -601,12 +599,11 @@ k_pass(Cx<T> *__restrict__ state, const __grid_constant__ PassGeom pg, const uin
                 const uint4 *const op_end = op + r0.y;   // r0.y = units of this round's op stream
 #pragma unroll 1
                 while (op != op_end) {
-                    const uint4 h0 = op[0], h1 = op[1];
+                    uint4 h0 = op[0], h1 = op[1];
                     const uint4 *pay = op + 2;
                     op += h0.x >> 16;
                     const uint32_t code = h0.x & 0xffffu;
                     uint32_t emask = h0.w;
-                    if (code != C_DIAGN && h1.z != 0xffffffffu) prefetch_l1(tables + h1.z + tid);   // G of the next phase group
                     int oi = 0;
                     if (code != C_PHASE && (h0.z != 0u || (h0.y & 0xffffu) != 0xffffu)) {   // predicated op
                         const uint32_t oslot = h0.y & 0xffffu, tmask = h0.z;
@@ -632,6 +629,21 @@ k_pass(Cx<T> *__restrict__ state, const __grid_constant__ PassGeom pg, const uin
 #undef QJ_D2
 #undef QJ_P2
                         case C_PHASE: {
+                          // A run of consecutive phase groups is handled here without going back to the
+                          // dispatcher, and the per-thread factor of the NEXT group is loaded before the
+                          // current one is applied (its latency hides behind the multiplies).
+                          Cx<T> gcur;
+                          gcur.re = T(1); gcur.im = T(0);
+                          if (h1.x != 0xffffffffu) gcur = ldg_cx(tables + h1.x + tid);
+                          for (;;) {
+                            const bool more = op != op_end && (op[0].x & 0xffffu) == uint32_t(C_PHASE);
+                            uint4 n0 = h0, n1 = h1;
+                            Cx<T> gnext;
+                            gnext.re = T(1); gnext.im = T(0);
+                            if (more) {
+                                n0 = op[0]; n1 = op[1];
+                                if (n1.x != 0xffffffffu) gnext = ldg_cx(tables + n1.x + tid);
+                            }
                             // h0.y = ntab | sel << 16, h0.z = all-sign flag; descriptors: 2 (<= 5 fields)
                             // or 3 units: {table, nf | oslot << 16, tmask, f0} {f1..f4} {f5..f8}
                             const int ntab = int(h0.y & 0xffffu);
@@ -646,9 +658,8 @@ k_pass(Cx<T> *__restrict__ state, const __grid_constant__ PassGeom pg, const uin
                             // h1.x: per-thread factor G[tid] (thread-only part, precomputed on the host:
                             // a thread's tile position is the same in every tile); h1.y: per-tile factor
                             if (h1.x != 0xffffffffu) {
-                                const Cx<T> z = ldg_cx(tables + h1.x + tid);
-                                if (allsign) sg ^= sign_of(z.re);
-                                else ph = z;
+                                if (allsign) sg ^= sign_of(gcur.re);
+                                else ph = gcur;
                                 have = true;
                             }
                             if (h1.y != 0xffffffffu) {
@@ -718,6 +729,13 @@ k_pass(Cx<T> *__restrict__ state, const __grid_constant__ PassGeom pg, const uin
                             }
                             if (allsign) phase_apply<T, true>(x, sel, emask, T(0), T(0), sg);
                             else phase_apply<T, false>(x, sel, emask, ph.re, ph.im, 0u);
+                            if (!more) break;
+                            h0 = n0; h1 = n1;
+                            pay = op + 2;
+                            op += n0.x >> 16;
+                            emask = n0.w;
+                            gcur = gnext;
+                          }
                         } break;
                         default: {  // C_DIAGN: table index = outer part | fields of the base | element part
                             const int nf = int(h0.y >> 16);
@@ -1530,7 +1548,7 @@ template <typename T>
 int launch_pass(qj_handle *h, const qj_program *p, void *state, const qj_program::Launch &L) {
     static bool configured = false;
     if (!configured) {
-        QJ_CUDA_OK(cudaFuncSetAttribute(k_pass<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 << 10));
+        QJ_CUDA_OK(cudaFuncSetAttribute(k_pass<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 << 10));
         configured = true;
     }
     // one thread per 16 vectors of the tile (at most 256); 128 registers per thread allow 512

@@ -1,0 +1,70 @@
+"""-m gpu tests of the distributed layer's device side on ONE rank: every gate becomes a
+LocalGate in shard numbering, the local segment is compiled into a pass program
+(`B200Backend.run_local_segment`) and must reproduce the einsum reference.  (The multi-rank NCCL
+path is exercised by tools/dist_check.py under torchrun; its logs are under profiles/.)"""
+
+import numpy as np
+import pytest
+
+from tests.gpu_utils import ATOL, backend
+from tests.test_distributed_cpu import _reference_state, _test_circuits
+
+pytestmark = pytest.mark.gpu
+
+
+class _OneRank:
+    rank, world = 0, 1
+
+    def barrier(self):
+        pass
+
+    def all_reduce_sum(self, t):
+        return t
+
+    def all_gather(self, t):
+        return [t]
+
+
+@pytest.mark.parametrize("dtype", ["complex128", "complex64"])
+@pytest.mark.parametrize("use_programs", [True, False])
+def test_single_rank_distributed_state_matches_reference(dtype, use_programs):
+    from qibojit_b200.distributed import DistributedState, LocalSegment
+
+    b = backend()
+    b.set_dtype(dtype)
+    b.use_programs = use_programs
+    try:
+        n = 13
+        for name, circuit in _test_circuits(n).items():
+            ds = DistributedState(b, n, comm=_OneRank(), dtype=dtype)
+            steps = ds.plan(circuit.queue)
+            assert all(isinstance(s, LocalSegment) for s in steps)
+            ds.run(steps)
+            got = ds.to_numpy_full()
+            ref = _reference_state(circuit, dtype)
+            np.testing.assert_allclose(got, ref, rtol=0, atol=ATOL[dtype], err_msg=name)
+            probs = b.to_numpy(ds.probabilities([0, n - 1, 2]))
+            p = (np.abs(ref.astype(np.complex128)) ** 2).reshape((2,) * n)
+            p = np.transpose(p.sum(axis=tuple(a for a in range(n) if a not in (0, n - 1, 2))), [0, 2, 1]).ravel()
+            np.testing.assert_allclose(probs, p, rtol=1e-5 if dtype == "complex64" else 1e-12, atol=1e-7, err_msg=name)
+            # the cached plan runs again from |0..0>
+            ds.reset()
+            ds.run(steps)
+            np.testing.assert_array_equal(ds.to_numpy_full(), got, err_msg=name)
+    finally:
+        b.use_programs = True
+        b.set_dtype("complex128")
+
+
+def test_measurement_leg_of_the_bench():
+    """bench.py's configs[4] leg (probabilities, 10^6 Metropolis shots, collapse) at a small size."""
+    import bench
+    from qibojit_b200 import circuits
+
+    b = backend()
+    b.set_dtype("complex128")
+    n = 16
+    state = b.execute_circuit(circuits.quantum_volume(n, depth=4))
+    out = bench.measurement_leg(b, state, n, "complex128", nshots=10 ** 6)
+    assert out["nshots"] == 10 ** 6 and out["distinct_outcomes"] > 1000
+    assert abs(out["norm_after_collapse"] - 1.0) < 1e-9
