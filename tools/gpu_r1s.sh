@@ -1,7 +1,7 @@
 #!/bin/bash
 set -x
 mkdir -p gpurun_out
-TAG=${TAG:-r1s}
+TAG=${TAG:-r1z}
 timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/${TAG}_pytest_gpu.log
 timeout 900 python bench.py > gpurun_out/${TAG}_bench_variational30.json 2> gpurun_out/${TAG}_bench_variational30.err; echo "bench rc=$?"; cat gpurun_out/${TAG}_bench_variational30.json; tail -5 gpurun_out/${TAG}_bench_variational30.err
 timeout 900 python bench.py --workload qv --steps 2 > gpurun_out/${TAG}_bench_qv32.json 2> gpurun_out/${TAG}_bench_qv32.err; echo "qv rc=$?"; cat gpurun_out/${TAG}_bench_qv32.json; tail -5 gpurun_out/${TAG}_bench_qv32.err
