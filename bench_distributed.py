@@ -38,6 +38,10 @@ class TimedBackend:
         return segment.compiled.run_timed(
             shard, lambda kind, frac, fn: self._timed(kind, 2.0 * self._nbytes * frac, fn))
 
+    def shard_exchange_multi(self, shard, nlocal, lbits, rank_bits, rank, comm, chunk_bytes=1 << 29):
+        return self._timed("exchange", self._nbytes * (1.0 - 2.0 ** -len(lbits)), self._b.shard_exchange_multi,
+                           shard, nlocal, lbits, rank_bits, rank, comm, chunk_bytes)
+
     def shard_exchange(self, shard, nlocal, lbit, peer, is_upper, comm, chunk_bytes=1 << 29):
         return self._timed("exchange", self._nbytes / 2, self._b.shard_exchange, shard, nlocal, lbit,
                            peer, is_upper, comm, chunk_bytes)
@@ -150,7 +154,8 @@ def run_distributed(args, backend, nqubits, dtype, fuse, world, rank):
                        "exchanges_per_step": stats["exchanges"] / args.steps,
                        "exchange_bytes_per_rank_per_step": stats["exchange_bytes"] / args.steps,
                        "parallelism": f"state sharded over {world} ranks on the top {world.bit_length() - 1} qubits, "
-                                      "NCCL pairwise half-shard swaps",
+                                      "NCCL qubit exchanges (pairwise half-shard swap for one qubit, "
+                                      "all-to-all of (2^k-1)/2^k of a shard for k qubits)",
                        "l2_policy": "shards are far larger than the 126 MB L2; no flush needed",
                        "timing": "CUDA events on the launch stream, max over ranks"},
             "roofline": {"bound": "hbm", "kernel": names.get(dom, dom), "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -149,6 +149,19 @@ int qj_swap_pack(qj_handle *h, const void *local, void *buf, int dtype, int nloc
                  int is_upper, int64_t chunk_begin, int64_t chunk_len);
 int qj_swap_unpack(qj_handle *h, void *local, const void *buf, int dtype, int nlocal, int m,
                    int is_upper, int64_t chunk_begin, int64_t chunk_len);
+/* Several global qubits at once (one all-to-all among the 2^nbits ranks that differ in the
+ * exchanged rank bits instead of nbits pairwise half-shard swaps: (2^nbits - 1) / 2^nbits of a
+ * shard crosses the links instead of nbits / 2).  pack: gather the sub-block of `local` whose
+ * index bits bits[i] (ascending) equal bit i of `value` -- the amplitudes that go to the rank
+ * whose exchanged rank bits spell `value` -- elements [chunk_begin, chunk_begin + chunk_len)
+ * of that sub-block, into contiguous `buf`; unpack: scatter what that rank sent into the same
+ * slots.  Generalises ops.swap_pieces (ops.py:131-137) to the piece transposition of
+ * ops.transpose_state / MultiGpuOps.to_pieces (gpu.py:1437-1465).                            */
+#define QJ_MAX_GLOBAL_SWAP 6
+int qj_swap_pack_bits(qj_handle *h, const void *local, void *buf, int dtype, int nlocal,
+                      const int32_t *bits, int nbits, int value, int64_t chunk_begin, int64_t chunk_len);
+int qj_swap_unpack_bits(qj_handle *h, void *local, const void *buf, int dtype, int nlocal,
+                        const int32_t *bits, int nbits, int value, int64_t chunk_begin, int64_t chunk_len);
 
 /* ---- multi-gate passes ("tile programs") ------------------------------------------------------
  * replaces a whole gate queue per device: the loop `for gate in queue: apply_gate(...)` of

@@ -46,6 +46,8 @@ SIGNATURES = {
     "qj_swap_pieces_peer": (_I, [_P, _P, _P, _I, _I, _I, _I]),
     "qj_swap_pack": (_I, [_P, _P, _P, _I, _I, _I, _I, _L, _L]),
     "qj_swap_unpack": (_I, [_P, _P, _P, _I, _I, _I, _I, _L, _L]),
+    "qj_swap_pack_bits": (_I, [_P, _P, _P, _I, _I, _P, _I, _I, _L, _L]),
+    "qj_swap_unpack_bits": (_I, [_P, _P, _P, _I, _I, _P, _I, _I, _L, _L]),
     "qj_program_create": (_I, [_P, _I, _I, _P, _I, _P, _L, _P, _L, _P, _L, _c.POINTER(_P)]),
     "qj_program_run": (_I, [_P, _P, _P]),
     "qj_program_run_launch": (_I, [_P, _P, _P, _I]),

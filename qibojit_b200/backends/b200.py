@@ -609,6 +609,48 @@ class B200Backend(_QiboBackend):
                                                      lbit, int(is_upper), c0, n))
         return half * esize
 
+    def shard_exchange_multi(self, shard, nlocal, lbits, rank_bits, rank, comm, chunk_bytes=1 << 29):
+        """Swap k global qubits (rank bits `rank_bits`) with k local ones (index bits `lbits`,
+        ascending, paired in order) in ONE all-to-all among the 2^k ranks that differ in those
+        rank bits: this rank sends the sub-block whose local bits spell `a` to the rank whose
+        exchanged rank bits spell `a`, and stores what that rank sends in the same slots.
+        (2^k - 1) / 2^k of the shard crosses the links instead of k / 2.  Chunked through a
+        bounded staging buffer.  Returns the bytes sent."""
+        dist = comm.dist
+        torch = _torch()
+        k = len(lbits)
+        mine = sum(((rank >> j) & 1) << i for i, j in enumerate(rank_bits))
+        others = [a for a in range(1 << k) if a != mine]
+        peers = {}
+        for a in others:
+            r = rank
+            for i, j in enumerate(rank_bits):
+                r = (r & ~(1 << j)) | (((a >> i) & 1) << j)
+            peers[a] = r
+        sub = 1 << (nlocal - k)
+        esize = shard.element_size()
+        chunk = max(2, min(sub, (chunk_bytes // esize // len(others)) & ~1023 or 2))   # whole 16-byte vectors
+        tag = self._tag(shard)
+        h = self._handle()
+        bits = np.ascontiguousarray(np.asarray(lbits, dtype=np.int32))
+        for c0 in range(0, sub, chunk):
+            n = min(chunk, sub - c0)
+            ops, bufs = [], []
+            for a in others:
+                send = self._staging(n, shard.dtype, ("send", a))
+                recv = self._staging(n, shard.dtype, ("recv", a))
+                _capi.check(self._lib.qj_swap_pack_bits(h, shard.data_ptr(), send.data_ptr(), tag, nlocal,
+                                                        bits.ctypes.data, k, a, c0, n))
+                ops.append(dist.P2POp(dist.isend, torch.view_as_real(send), peers[a], group=comm.group))
+                ops.append(dist.P2POp(dist.irecv, torch.view_as_real(recv), peers[a], group=comm.group))
+                bufs.append((a, recv))
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+            for a, recv in bufs:
+                _capi.check(self._lib.qj_swap_unpack_bits(h, shard.data_ptr(), recv.data_ptr(), tag, nlocal,
+                                                          bits.ctypes.data, k, a, c0, n))
+        return len(others) * sub * esize
+
     # ------------------------------------------------------------------ circuits
     def execute_circuit(self, circuit, initial_state=None, nshots=None):
         """Stand-in for qibo's ``Backend.execute_circuit``: zero state (or a

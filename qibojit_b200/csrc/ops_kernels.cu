@@ -436,6 +436,30 @@ k_swap_pack(const float4 *__restrict__ local, float4 *__restrict__ buf, int mv, 
     }
 }
 
+// sub-block of a shard selected by several index bits: group g -> vector index with zeros
+// inserted at pos[] (ascending vector-level positions), OR the fixed bit values
+struct SubBlock {
+    int npos;
+    int pos[QJ_MAX_GLOBAL_SWAP];
+    int64_t ormask;
+};
+__global__ void __launch_bounds__(kThreads)
+k_swap_pack_bits(const float4 *__restrict__ local, float4 *__restrict__ buf, const __grid_constant__ SubBlock sb,
+                 int64_t g_begin, int64_t count, int unpack) {
+    const int64_t stride = int64_t(gridDim.x) * kThreads;
+    for (int64_t k = int64_t(blockIdx.x) * kThreads + threadIdx.x; k < count; k += stride) {
+        int64_t i = g_begin + k;
+#pragma unroll 1
+        for (int j = 0; j < sb.npos; j++) {
+            const int p = sb.pos[j];
+            i = ((i >> p) << (p + 1)) | (i & ((int64_t(1) << p) - 1));
+        }
+        i |= sb.ormask;
+        if (unpack) const_cast<float4 *>(local)[i] = buf[k];
+        else buf[k] = local[i];
+    }
+}
+
 template <typename F>
 int launch_checked(qj_handle *h, F &&f) {
     f();
@@ -765,4 +789,41 @@ extern "C" int qj_swap_pack(qj_handle *h, const void *local, void *buf, int dtyp
 extern "C" int qj_swap_unpack(qj_handle *h, void *local, const void *buf, int dtype, int nlocal, int m,
                               int is_upper, int64_t chunk_begin, int64_t chunk_len) {
     return swap_pack_impl(h, local, const_cast<void *>(buf), dtype, nlocal, m, is_upper, chunk_begin, chunk_len, 1);
+}
+
+namespace {
+int swap_pack_bits_impl(qj_handle *h, const void *local, void *buf, int dtype, int nlocal, const int32_t *bits,
+                        int nbits, int value, int64_t begin, int64_t len, int unpack) {
+    QJ_REQUIRE(h && local && buf && bits, "null argument");
+    QJ_REQUIRE(nbits >= 1 && nbits <= QJ_MAX_GLOBAL_SWAP && nbits < nlocal, "bad number of exchange bits");
+    QJ_REQUIRE(value >= 0 && value < (1 << nbits), "sub-block value out of range");
+    const int v = (dtype == QJ_C128) ? 0 : 1;
+    SubBlock sb;
+    sb.npos = nbits;
+    sb.ormask = 0;
+    for (int i = 0; i < nbits; i++) {
+        if (bits[i] < v) return fail(QJ_ERR_UNSUPPORTED, "swap on index bit 0 of a complex64 shard: choose another local partner bit");
+        QJ_REQUIRE(bits[i] < nlocal && (i == 0 || bits[i] > bits[i - 1]), "exchange bits must be ascending and below nlocal");
+        sb.pos[i] = bits[i] - v;
+        if ((value >> i) & 1) sb.ormask |= int64_t(1) << (bits[i] - v);
+    }
+    QJ_REQUIRE(begin >= 0 && len >= 0 && ((begin | len) & ((1 << v) - 1)) == 0, "chunk must be vector aligned");
+    const int64_t gb = begin >> v, cnt = len >> v;
+    QJ_REQUIRE(gb + cnt <= (int64_t(1) << (nlocal - v - nbits)), "chunk outside the sub-block");
+    if (cnt == 0) return QJ_OK;
+    return launch_checked(h, [&] {
+        k_swap_pack_bits<<<persistent_grid(h, cnt, kThreads * 4), kThreads, 0, h->stream>>>(
+            reinterpret_cast<const float4 *>(local), reinterpret_cast<float4 *>(buf), sb, gb, cnt, unpack);
+    });
+}
+}  // namespace
+
+extern "C" int qj_swap_pack_bits(qj_handle *h, const void *local, void *buf, int dtype, int nlocal,
+                                 const int32_t *bits, int nbits, int value, int64_t chunk_begin, int64_t chunk_len) {
+    return swap_pack_bits_impl(h, local, buf, dtype, nlocal, bits, nbits, value, chunk_begin, chunk_len, 0);
+}
+extern "C" int qj_swap_unpack_bits(qj_handle *h, void *local, const void *buf, int dtype, int nlocal,
+                                   const int32_t *bits, int nbits, int value, int64_t chunk_begin, int64_t chunk_len) {
+    return swap_pack_bits_impl(h, local, const_cast<void *>(buf), dtype, nlocal, bits, nbits, value, chunk_begin,
+                               chunk_len, 1);
 }

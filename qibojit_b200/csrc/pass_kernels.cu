@@ -12,21 +12,29 @@
 //     complex64: J = 5, index bit 0 -- the second amplitude of a vector -- always being one of
 //     them).  It gathers them from shared memory, applies every op of the round in registers,
 //     and scatters them back: shared memory is read and written once per round, not per gate.
-//   * ops: dense 2x2 / 4x4 on register slots (controls may be register slots -> element mask,
-//     other tile bits -> thread predicate, bits outside the tile -> tile predicate), X / SWAP as
-//     register renaming, and diagonal phase tables.  A table is sliced on the host along its
-//     register bits, so a slice is ONE look-up per thread (index = fields of the thread's tile
-//     position | a tile-constant part) followed by a complex multiply of the selected elements;
-//     +-1 tables become sign flips.
+//   * ops: one-target gates on a SET of register slots (one dispatch for up to J gates of a
+//     kind: complex / real / real-diagonal + imaginary-off-diagonal), dense 4x4 on two slots,
+//     X / SWAP as register renaming, and phase groups.  Controls may be register slots
+//     (-> element mask), other tile bits (-> thread predicate) or bits outside the tile
+//     (-> tile predicate); a failed predicate zeroes the element mask, so the op loop has
+//     warp-uniform control flow only.
+//   * phase groups: the diagonal tables of a run that multiply the same elements are one op,
+//     phase = G[tid] * H[tile] * (mixed per-thread look-ups).  G is the product of the tables
+//     over tile-local bits only, precomputed on the host per thread (a thread's tile position
+//     is the same in every tile); H is the product of the tables over outer bits only, computed
+//     once per tile.  +-1 factors are sign flips.  Consecutive groups run inside one dispatch.
+//   * complex64 arithmetic is packed FP32x2 (FFMA2 / FMUL2): an amplitude is one 64-bit operand.
 //   * the whole program (rounds, op headers, gate matrices) is copied to shared memory once
-//     per CTA and read with warp-uniform (broadcast) loads; only phase tables stay in global
-//     memory (L1-resident).
+//     per CTA and read with warp-uniform (broadcast) loads; tables and G stay in global memory
+//     (L1, evict_last).
 //   * shared-memory layout: 16-byte vectors, XOR swizzle of the low three vector-index bits with
 //     the three-bit groups above them; the host orders the thread bits of every round so that
 //     the eight lanes of a quarter warp hit eight different bank groups whatever the register
-//     bits are.
-//   * 256 threads and one 64 KiB tile per CTA, two CTAs per SM: while one CTA waits for its
-//     tile (LDGSTS) or drains its stores the other one computes.
+//     bits are.  Tile IO (cp.async in, LDS + STG out) splits its address arithmetic into a
+//     per-thread and a warp-uniform part (the swizzle is XOR-linear).
+//   * one thread per 16 vectors of the tile, 128 registers: complex128 runs four 128-thread
+//     CTAs with 32 KiB tiles per SM, complex64 two 256-thread CTAs with 64 KiB tiles; while one
+//     CTA waits for its tile or drains its stores the others compute.
 //
 // Arithmetic contract per op: gates.py:16-38 (one target), gates.py:118-193 (two targets),
 // gates.py:82-114 (diagonals, pre-multiplied into tables on the host).
@@ -1433,21 +1441,6 @@ extern "C" int qj_program_create(qj_handle *h, int dtype, int nqubits, const qj_
 
             flush_pending();
 
-            // prefetch links: every op names the per-thread factor table of the next phase group
-            uint32_t first_g = 0xffffffffu;
-            {
-                std::vector<size_t> starts;
-                for (size_t i = 0; i < r_ops.size(); i += r_ops[i].w[0] >> 16) starts.push_back(i);
-                uint32_t next_g = 0xffffffffu;
-                for (size_t k = starts.size(); k-- > 0;) {
-                    const size_t i = starts[k];
-                    const uint32_t code = r_ops[i].w[0] & 0xffffu;
-                    if (code != uint32_t(C_DIAGN)) r_ops[i + 1].w[2] = next_g;
-                    if (code == uint32_t(C_PHASE) && r_ops[i + 1].w[0] != 0xffffffffu) next_g = r_ops[i + 1].w[0];
-                }
-                first_g = next_g;
-            }
-
             // append the round (closing the launch first when the image would overflow)
             const size_t need_units = 2 + round_units.size() + 3 + outer_units.size() + r_outer.size() + h_units.size() +
                                       r_H.size() + op_units.size() + r_ops.size() + (h_units.size() + r_H.size()) / 4;
@@ -1491,7 +1484,6 @@ extern "C" int qj_program_create(qj_handle *h, int dtype, int nqubits, const qj_
                     u1.w[kbit >> 1] |= td << ((kbit & 1) * 16);
                     u2.w[kbit >> 2] |= uint32_t(tq[kbit] + VS) << ((kbit & 3) * 8);
                 }
-                u2.w[2] = first_g;
                 round_units.push_back(u0); round_units.push_back(u1); round_units.push_back(u2);
                 outer_units.insert(outer_units.end(), r_outer.begin(), r_outer.end());
                 h_units.insert(h_units.end(), r_H.begin(), r_H.end());

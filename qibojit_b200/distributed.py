@@ -142,6 +142,16 @@ class Exchange:
         self.local_bit = int(local_bit)
 
 
+class MultiExchange:
+    """Swap rank bits `rank_bits[i]` with shard index bits `local_bits[i]` (ascending) in one
+    all-to-all among the 2^k ranks that differ in those rank bits."""
+
+    def __init__(self, rank_bits, local_bits):
+        pairs = sorted(zip(local_bits, rank_bits))
+        self.local_bits = [int(l) for l, _ in pairs]
+        self.rank_bits = [int(j) for _, j in pairs]
+
+
 class DistributedState:
     """A 2^nqubits state vector sharded over the ranks of `comm`."""
 
@@ -219,6 +229,19 @@ class DistributedState:
         assert gbit >= self.nlocal > lbit
         plan.append(Exchange(gbit - self.nlocal, lbit))
         self.bit_of[qglobal], self.bit_of[qlocal] = lbit, gbit
+
+    def _plan_multi_exchange(self, plan, pairs):
+        """pairs: [(global qubit, local qubit)]; one pair degenerates to a plain Exchange."""
+        if len(pairs) == 1:
+            return self._plan_exchange(plan, *pairs[0])
+        rank_bits, local_bits = [], []
+        for qg, ql in pairs:
+            gbit, lbit = self.bit_of[qg], self.bit_of[ql]
+            assert gbit >= self.nlocal > lbit
+            rank_bits.append(gbit - self.nlocal)
+            local_bits.append(lbit)
+            self.bit_of[qg], self.bit_of[ql] = lbit, gbit
+        plan.append(MultiExchange(rank_bits, local_bits))
 
     def _plan_gate(self, plan, gate, lookahead):
         """Symbolic application of one gate: updates the qubit map and appends this rank's local
@@ -314,7 +337,7 @@ class DistributedState:
         else:
             self._emit_phase(plan, complex(d[0]), lcontrols)
 
-    def plan(self, queue, reorder=True, free_initial_map=None):
+    def plan(self, queue, reorder=True, free_initial_map=None, batch_exchanges=True):
         """Gate list -> [LocalSegment | Exchange] for this rank, advancing the qubit map.  The
         exchange steps are identical on every rank (they depend on the map and the gate list
         only); the local gates differ by the rank predicates.
@@ -325,6 +348,9 @@ class DistributedState:
         fewest remaining gates that need it local (a finished qubit costs no later exchange),
         ties broken by the farthest next use.  `reorder=False` keeps program order with a
         look-ahead victim choice.
+
+        `batch_exchanges`: when several global qubits block ready gates at once they are swapped
+        in together (`MultiExchange`); False swaps one qubit at a time.
 
         `free_initial_map` (default: True while the state is still |0...0>, which is symmetric
         under qubit relabelling): the qubits whose first non-diagonal gate comes latest start as
@@ -415,18 +441,37 @@ class DistributedState:
                     blocked.append(i)
             if ndone == len(gates):
                 break
-            # nothing can run: bring in the qubits of the earliest blocked gate
+            # nothing can run: bring in, in ONE exchange, every global qubit that a blocked ready
+            # gate needs (an all-to-all over k qubits moves (2^k - 1) / 2^k of a shard, k separate
+            # swaps k / 2)
             assert blocked, "dependency cycle in the gate list"
-            i = min(blocked)
             for q in uses:
                 while upos[q] < len(uses[q]) and done[uses[q][upos[q]]]:
                     upos[q] += 1
-            for q in needs[i]:
-                if self.is_local(q):
-                    continue
+            wanted, keep = [], set()
+            for i in sorted(blocked):
+                keep.update(needs[i])
+                for q in needs[i]:
+                    if not self.is_local(q) and q not in wanted:
+                        wanted.append(q)
+            if not batch_exchanges:
+                wanted = wanted[:1]
+                keep = set(needs[min(blocked)])
+            else:
+                # global qubits that are needed later ride along for free when a FINISHED local
+                # qubit can take their place (it never has to come back)
+                finished = [v for v in range(self.nqubits) if self.is_local(v) and v not in keep
+                            and len(uses[v]) == upos[v]
+                            and not (self.dtype == "complex64" and self.bit_of[v] == 0)]
+                later = sorted((q for q in range(self.nqubits) if not self.is_local(q) and q not in wanted
+                                and len(uses[q]) > upos[q]), key=lambda q: uses[q][upos[q]])
+                spare = len(finished) - len(wanted)
+                wanted.extend(later[:max(0, spare)])
+            pairs, taken = [], set()
+            for q in wanted:
                 best, best_key = None, None
                 for v in range(self.nqubits):
-                    if not self.is_local(v) or v in needs[i]:
+                    if not self.is_local(v) or v in keep or v in taken:
                         continue
                     if self.dtype == "complex64" and self.bit_of[v] == 0:
                         continue  # 16-byte exchange granularity
@@ -436,8 +481,12 @@ class DistributedState:
                     if best is None or key < best_key:
                         best, best_key = v, key
                 if best is None:
+                    if pairs:
+                        break           # fewer victims than wanted qubits: the rest waits
                     raise RuntimeError("no local qubit available to swap with")
-                self._plan_exchange(steps, q, best)
+                taken.add(best)
+                pairs.append((q, best))
+            self._plan_multi_exchange(steps, pairs)
             for j in blocked:
                 heapq.heappush(ready, j)
             blocked = []
@@ -458,6 +507,11 @@ class DistributedState:
             if isinstance(step, LocalSegment):
                 self.shard = b.run_local_segment(self.shard, self.nlocal, step)
                 self.stats["local_segments"] += 1
+            elif isinstance(step, MultiExchange):
+                moved = b.shard_exchange_multi(self.shard, self.nlocal, step.local_bits, step.rank_bits,
+                                               self.rank, self.comm, self.swap_chunk_bytes)
+                self.stats["exchanges"] += 1
+                self.stats["exchange_bytes"] += int(moved)
             else:
                 peer = self.rank ^ (1 << step.rank_bit)
                 moved = b.shard_exchange(self.shard, self.nlocal, step.local_bit, peer,

@@ -97,3 +97,31 @@ class OracleBackend:
             dist.send(send, peer, group=comm.group)
         shard[sel] = torch.view_as_complex(recv)
         return send.numel() * send.element_size()
+
+    def shard_exchange_multi(self, shard, nlocal, lbits, rank_bits, rank, comm, chunk_bytes=1 << 29):
+        """Pairwise sub-block swaps in XOR-distance order (both partners meet at the same step)."""
+        dist = comm.dist
+        k = len(lbits)
+        mine = sum(((rank >> j) & 1) << i for i, j in enumerate(rank_bits))
+        idx = np.arange(1 << nlocal)
+        field = np.zeros_like(idx)
+        for i, l in enumerate(lbits):
+            field |= ((idx >> l) & 1) << i
+        moved = 0
+        for d in range(1, 1 << k):
+            a = mine ^ d
+            peer = rank
+            for i, j in enumerate(rank_bits):
+                peer = (peer & ~(1 << j)) | (((a >> i) & 1) << j)
+            sel = torch.from_numpy(idx[field == a])
+            send = torch.view_as_real(shard[sel].contiguous())
+            recv = torch.empty_like(send)
+            if rank < peer:
+                dist.send(send, peer, group=comm.group)
+                dist.recv(recv, peer, group=comm.group)
+            else:
+                dist.recv(recv, peer, group=comm.group)
+                dist.send(send, peer, group=comm.group)
+            shard[sel] = torch.view_as_complex(recv)
+            moved += send.numel() * send.element_size()
+        return moved

@@ -75,6 +75,10 @@ def _worker(rank, world, port, n, dtype, q, via_planner=False):
             ds.reset()
             ds.run(steps)
             assert np.array_equal(ds.to_numpy_full(), full), name
+            ds3 = DistributedState(b, n, comm=Comm(), dtype=dtype)
+            ds3.run(ds3.plan(circuit.queue, batch_exchanges=False))
+            np.testing.assert_allclose(ds3.to_numpy_full(), full, rtol=0,
+                                       atol=1e-5 if dtype == "complex64" else 1e-12, err_msg=name)
             ds2 = DistributedState(b, n, comm=Comm(), dtype=dtype)
             ds2.run(ds2.plan(circuit.queue, reorder=False))
             np.testing.assert_allclose(ds2.to_numpy_full(), full, rtol=0,
@@ -86,8 +90,10 @@ def _worker(rank, world, port, n, dtype, q, via_planner=False):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,n,via_planner", [(2, 6, False), (4, 7, False), (2, 8, True), (4, 9, True)])
-@pytest.mark.parametrize("dtype", ["complex128", "complex64"])
+@pytest.mark.parametrize("world,n,via_planner,dtype", [
+    (2, 6, False, "complex128"), (2, 6, False, "complex64"), (4, 7, False, "complex128"), (4, 7, False, "complex64"),
+    (8, 8, False, "complex128"),          # three global qubits: 8-way all-to-all exchange
+    (2, 8, True, "complex128"), (2, 8, True, "complex64"), (4, 9, True, "complex128"), (4, 9, True, "complex64")])
 def test_distributed_state_matches_single_state(world, n, via_planner, dtype):
     """via_planner: each rank's local segments are lowered by planner.plan_queue (what the B200
     backend compiles into pass programs) and interpreted in numpy, instead of gate by gate."""
@@ -112,7 +118,7 @@ def test_distributed_state_matches_single_state(world, n, via_planner, dtype):
         np.testing.assert_allclose(probs, p, rtol=0, atol=1e-5 if dtype == "complex64" else 1e-12, err_msg=name)
         assert abs(norm2 - float(np.vdot(ref, ref).real)) < 1e-4
     # the QFT's controlled phases and final swaps must not trigger exchanges beyond the H gates
-    assert results["qft"][2]["exchanges"] <= int(np.log2(world)) + 1
+    assert results["qft"][2]["exchanges"] == 1       # one (multi-)exchange whatever the world size
     assert results["qft"][2]["relabelled_swaps"] == n // 2
 
 
@@ -150,16 +156,27 @@ def test_dag_schedule_needs_few_exchanges():
             return None
 
     def count(circuit, n, world, dtype, **kw):
+        """(number of exchange steps, shards moved) -- identical on every rank."""
+        from qibojit_b200.distributed import MultiExchange
+
         per_rank = []
         for rank in (0, world - 1):
             ds = DistributedState(NoAlloc(dtype), n, comm=FakeComm(rank, world), dtype=dtype)
             steps = ds.plan(circuit.queue, **kw)
-            per_rank.append([(s.rank_bit, s.local_bit) for s in steps if isinstance(s, Exchange)])
+            sig = []
+            for s in steps:
+                if isinstance(s, Exchange):
+                    sig.append(((s.rank_bit,), (s.local_bit,)))
+                elif isinstance(s, MultiExchange):
+                    sig.append((tuple(s.rank_bits), tuple(s.local_bits)))
+            per_rank.append(sig)
         assert per_rank[0] == per_rank[1]      # every rank plans the same exchanges
-        return len(per_rank[0])
+        return len(per_rank[0]), sum(1 - 2.0 ** -len(r) for r, _ in per_rank[0])
 
-    assert count(circuits.variational(30), 30, 2, "complex128") == 1
-    assert count(circuits.variational(30), 30, 2, "complex128", reorder=False) >= 5
-    assert count(circuits.qft(34), 34, 2, "complex128") == 1
-    assert count(circuits.supremacy(36), 36, 8, "complex64") == 3
-    assert count(circuits.qft(36), 36, 8, "complex64") == 3
+    assert count(circuits.variational(30), 30, 2, "complex128") == (1, 0.5)
+    assert count(circuits.variational(30), 30, 2, "complex128", reorder=False)[0] >= 5
+    assert count(circuits.qft(34), 34, 2, "complex128") == (1, 0.5)
+    # three global qubits: one all-to-all (7/8 of a shard) instead of three swaps (3/2)
+    assert count(circuits.supremacy(36), 36, 8, "complex64") == (1, 0.875)
+    assert count(circuits.qft(36), 36, 8, "complex64") == (1, 0.875)
+    assert count(circuits.supremacy(36), 36, 8, "complex64", batch_exchanges=False) == (3, 1.5)

@@ -153,3 +153,44 @@ def test_sample_shots_matches_numpy_choice():
     np.random.seed(77)
     expect = np.random.choice(len(probs), size=5000, p=probs)
     assert (shots == expect).mean() > 0.999  # cumsum association may flip a boundary ulp
+
+
+@pytest.mark.parametrize("dtype", ["complex128", "complex64"])
+def test_swap_pack_bits_roundtrip(dtype):
+    """qj_swap_pack_bits gathers the sub-block selected by several index bits (the piece that goes
+    to one peer of a multi-qubit exchange), qj_swap_unpack_bits scatters into the same slots."""
+    import torch
+
+    from qibojit_b200 import _capi
+
+    b = backend()
+    nlocal = 12
+    rng = np.random.default_rng(5)
+    host = (rng.standard_normal(1 << nlocal) + 1j * rng.standard_normal(1 << nlocal)).astype(dtype)
+    shard = b.cast(host, dtype=dtype, copy=True)
+    tag = b._tag(shard)
+    for bits, value in [([3, 7], 2), ([1, 5, 11], 5), ([2], 1), ([4, 6, 8, 10], 9)]:
+        k = len(bits)
+        idx = np.arange(1 << nlocal)
+        field = np.zeros_like(idx)
+        for i, l in enumerate(bits):
+            field |= ((idx >> l) & 1) << i
+        sel = idx[field == value]
+        sub = 1 << (nlocal - k)
+        barr = np.asarray(bits, dtype=np.int32)
+        buf = torch.empty(sub, dtype=shard.dtype, device=shard.device)
+        half = sub // 2
+        for c0, n in ((0, half), (half, sub - half)):       # two chunks
+            _capi.check(b._lib.qj_swap_pack_bits(b._handle(), shard.data_ptr(), buf[c0:].data_ptr(), tag, nlocal,
+                                                 barr.ctypes.data, k, value, c0, n))
+        np.testing.assert_array_equal(b.to_numpy(buf), host[sel])
+        repl = (rng.standard_normal(sub) + 1j * rng.standard_normal(sub)).astype(dtype)
+        src = b.cast(repl, dtype=dtype, copy=True)
+        _capi.check(b._lib.qj_swap_unpack_bits(b._handle(), shard.data_ptr(), src.data_ptr(), tag, nlocal,
+                                               barr.ctypes.data, k, value, 0, sub))
+        host[sel] = repl
+        np.testing.assert_array_equal(b.to_numpy(shard), host)
+    with pytest.raises(ValueError):
+        barr = np.asarray([5, 3], dtype=np.int32)           # not ascending
+        _capi.check(b._lib.qj_swap_pack_bits(b._handle(), shard.data_ptr(), shard.data_ptr(), tag, nlocal,
+                                             barr.ctypes.data, 2, 0, 0, 2))
