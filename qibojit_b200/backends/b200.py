@@ -629,26 +629,42 @@ class B200Backend(_QiboBackend):
             peers[a] = r
         sub = 1 << (nlocal - k)
         esize = shard.element_size()
-        chunk = max(2, min(sub, (chunk_bytes // esize // len(others)) & ~1023 or 2))   # whole 16-byte vectors
+        # two chunk slots: chunk c + 1 is packed (and its transfers queued) while chunk c is on
+        # the links, chunk c is unpacked while chunk c + 1 travels
+        chunk = max(2, min(sub, (chunk_bytes // esize // len(others) // 2) & ~1023 or 2))   # whole 16-byte vectors
         tag = self._tag(shard)
         h = self._handle()
         bits = np.ascontiguousarray(np.asarray(lbits, dtype=np.int32))
-        for c0 in range(0, sub, chunk):
+
+        def launch(c0, slot):
             n = min(chunk, sub - c0)
             ops, bufs = [], []
             for a in others:
-                send = self._staging(n, shard.dtype, ("send", a))
-                recv = self._staging(n, shard.dtype, ("recv", a))
+                send = self._staging(n, shard.dtype, ("send", a, slot))
+                recv = self._staging(n, shard.dtype, ("recv", a, slot))
                 _capi.check(self._lib.qj_swap_pack_bits(h, shard.data_ptr(), send.data_ptr(), tag, nlocal,
                                                         bits.ctypes.data, k, a, c0, n))
                 ops.append(dist.P2POp(dist.isend, torch.view_as_real(send), peers[a], group=comm.group))
                 ops.append(dist.P2POp(dist.irecv, torch.view_as_real(recv), peers[a], group=comm.group))
                 bufs.append((a, recv))
-            for req in dist.batch_isend_irecv(ops):
+            return c0, n, dist.batch_isend_irecv(ops), bufs
+
+        def finish(job):
+            c0, n, reqs, bufs = job
+            for req in reqs:
                 req.wait()
             for a, recv in bufs:
                 _capi.check(self._lib.qj_swap_unpack_bits(h, shard.data_ptr(), recv.data_ptr(), tag, nlocal,
                                                           bits.ctypes.data, k, a, c0, n))
+
+        pending = None
+        for i, c0 in enumerate(range(0, sub, chunk)):
+            job = launch(c0, i & 1)
+            if pending is not None:
+                finish(pending)
+            pending = job
+        if pending is not None:
+            finish(pending)
         return len(others) * sub * esize
 
     # ------------------------------------------------------------------ circuits
