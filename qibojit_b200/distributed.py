@@ -14,14 +14,22 @@ Rules:
   (ii)  control on a global qubit        -> only ranks whose bit is 1 run it, control dropped
   (iii) diagonal gate on a global target -> restricted to the rank's bit value: a smaller local
         diagonal gate or a scalar phase on the shard; no exchange
-  (iv)  anything else                    -> swap the global qubit with a local one first
-        (``swap_pieces`` semantics), choosing the local qubit whose next use is farthest away
-  SWAP gates are executed by relabelling the qubit map (no data movement at all).
+  (iv)  anything else                    -> the global qubit is swapped with a local one first
+        (``swap_pieces`` semantics)
+  SWAP gates are executed by relabelling the qubit map (no data movement at all), and so is the
+  choice of the initial layout of |0...0>.
+
+Scheduling (``DistributedState.plan``): the gate list is walked as its dependency DAG -- every
+ready gate that needs no exchange runs first -- and when nothing else can run ALL global qubits
+that block (plus later-needed ones that can displace finished local qubits) are exchanged in one
+all-to-all among the ranks that differ in those rank bits.  The plan is a list of
+``LocalSegment`` (this rank's gates in shard numbering, compiled by the backend into multi-gate
+pass programs), ``Exchange`` (one qubit, half a shard each way) and ``MultiExchange`` steps.
 
 The class talks to the device only through the backend's reference-style kernel entry points
-(``_one_qubit_base`` ...) plus three shard primitives of the backend (``shard_zeros``,
-``shard_scale``, ``shard_exchange``), so the same logic runs on gloo/CPU in the tests with a
-numpy stand-in backend.
+(``_one_qubit_base`` ...) plus a few shard primitives of the backend (``shard_zeros``,
+``shard_reset``, ``run_local_segment``, ``shard_exchange``, ``shard_exchange_multi``), so the same
+logic runs on gloo/CPU in the tests with a numpy stand-in backend.
 """
 
 import numpy as np

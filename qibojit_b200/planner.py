@@ -463,6 +463,9 @@ class Program:
                         axis = not (m[0, 0].imag or m[1, 1].imag or m[0, 1].real or m[1, 0].real)
                         total += (4.0 if (real or axis) else 8.0) * frac
                     elif op.kind == "dense":
+                        m = d.reshape(4, 4)
+                        if np.array_equal(m, [[1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]]):
+                            continue            # SWAP: register renaming
                         total += 16.0 * frac
                     elif op.kind == "diag":
                         if np.all((d.imag == 0) & (np.abs(d.real) == 1)):

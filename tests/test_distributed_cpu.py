@@ -55,6 +55,7 @@ def _test_circuits(n):
 
 def _worker(rank, world, port, n, dtype, q, via_planner=False):
     sys.path.insert(0, ROOT)
+    os.environ["OMP_NUM_THREADS"] = "1"      # `world` ranks share the host cores
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)

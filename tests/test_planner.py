@@ -110,3 +110,39 @@ def test_phase_tables_are_split_by_locality():
                     continue
                 rest = op.bits - set(regs)
                 assert rest <= local or not (rest & local), (sorted(rest), sorted(local))
+
+
+def test_fma_count_of_the_benchmark_circuits():
+    """The arithmetic side of the roofline bench.py reports: 4 real FMAs per amplitude for a real
+    or axis-aligned one-qubit gate, 8 for a complex one, 16 for a 4x4, none for sign flips."""
+    class Stub(planner.Program):
+        def __init__(self, queue, n, dt):
+            self.passes = [(s[1], s[2]) for s in planner.plan_queue(
+                queue, n, CustomMatrices(dt), planner.DEFAULT_TILE_BITS[dt], planner.DEFAULT_RUN_BITS[dt], 10, dt)
+                if s[0] == "pass"]
+            self.segments = []
+
+    n = 20
+    assert Stub(circuits.variational(n).queue, n, "complex128").fma_per_amplitude() == 5 * n * 4    # RY real, CZ = signs
+    qv = circuits.quantum_volume(n, depth=3)
+    assert Stub(qv.queue, n, "complex64").fma_per_amplitude() == len(qv.queue) * 16
+    assert Stub([gates.X(0), gates.CNOT(1, 2), gates.SWAP(3, 4), gates.Z(5)], n, "complex128").fma_per_amplitude() == 0
+
+
+def test_local_gates_of_the_distributed_layer_lower_like_their_originals():
+    """distributed.LocalGate carries a dense target matrix: the planner must classify it
+    (diagonal / dense / raw) exactly as it does the gate it came from."""
+    from qibojit_b200 import fusion
+    from qibojit_b200.distributed import LocalGate
+
+    n = 10
+    for g in [gates.H(2), gates.CU1(1, 3, 0.3), gates.RZ(4, 0.2), gates.CNOT(0, 5), gates.fSim(1, 2, 0.3, 0.4),
+              gates.TOFFOLI(0, 1, 2), gates.RZZ(3, 6, 0.5)]:
+        dense = fusion.target_only_matrix(g, MATS)
+        lg = LocalGate(None, g.target_qubits, g.control_qubits, dense, dense)
+        a = planner.lower_gate(g, n, MATS)
+        b = planner.lower_gate(lg, n, MATS)
+        assert [op.kind for op in a] == [op.kind for op in b]
+        for x, y in zip(a, b):
+            assert x.targets == y.targets and x.controls == y.controls
+            np.testing.assert_allclose(np.asarray(x.data), np.asarray(y.data), atol=1e-15)
