@@ -680,7 +680,8 @@ class B200Backend(_QiboBackend):
         else:
             state = self.cast(initial_state, copy=True)
         if getattr(self, "use_programs", True) and nqubits >= 4 and len(circuit.queue) > 1:
-            return self.compile_circuit(circuit).run(state)
+            # from |0...0> the SWAP gates of the circuit are relabellings (planner.relabel_swaps_away)
+            return self.compile_circuit(circuit, zero_state=initial_state is None).run(state)
         for gate in circuit.queue:
             state = gate.apply(self, state, nqubits)
         return state

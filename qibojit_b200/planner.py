@@ -301,11 +301,39 @@ def merge_round_diagonals(ops, reg_bits, max_diag_bits, local_bits=None):
     return out
 
 
-def plan_queue(queue, nqubits, matrices, tile_bits, run_bits, max_diag_bits=10, dtype="complex128"):
-    """Gate queue -> [('pass', local_bits, [(reg_bits, [PlanOp])]) | ('raw', gate)] (host logic)."""
+_SWAP_MATRIX = np.array([[1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]], dtype=np.complex128)
+
+
+def relabel_swaps_away(ops, nqubits):
+    """For a circuit that starts from |0...0>: drop every uncontrolled SWAP and relabel the ops
+    BEFORE it instead.  g_k ... g_1 with g_k = SWAP(a, b) equals (g'_{k-1} ... g'_1) SWAP(a, b)
+    where g' is g with a and b exchanged; the SWAP then acts on |0...0>, which it leaves alone.
+    (The distributed layer does the same with its qubit map.)  Returns `ops` unchanged when a raw
+    gate (whose qubits cannot be relabelled here) is present."""
+    if any(op.kind == "raw" for op in ops):
+        return ops
+    perm = list(range(nqubits))     # index bit -> relabelled index bit, for the ops still to come (going backwards)
+    out = []
+    for op in reversed(ops):
+        if (op.kind == "dense" and len(op.targets) == 2 and not op.controls
+                and np.array_equal(np.asarray(op.data).reshape(4, 4), _SWAP_MATRIX)):
+            a, b = perm[op.targets[0]], perm[op.targets[1]]
+            perm = [b if x == a else a if x == b else x for x in perm]
+            continue
+        out.append(PlanOp(op.kind, [perm[t] for t in op.targets], [perm[c] for c in op.controls], op.data, op.gate))
+    out.reverse()
+    return out
+
+
+def plan_queue(queue, nqubits, matrices, tile_bits, run_bits, max_diag_bits=10, dtype="complex128",
+               zero_state=False):
+    """Gate queue -> [('pass', local_bits, [(reg_bits, [PlanOp])]) | ('raw', gate)] (host logic).
+    `zero_state`: the program will only ever run on |0...0> (SWAP gates become relabellings)."""
     ops = []
     for gate in queue:
         ops.extend(lower_gate(gate, nqubits, matrices))
+    if zero_state:
+        ops = relabel_swaps_away(ops, nqubits)
     nreg = REG_BITS[str(dtype)]
     fixed = (0,) if str(dtype) == "complex64" else ()
     mdb = min(max_diag_bits, _capi.QJ_MAX_DIAG_BITS)
@@ -330,8 +358,9 @@ class Program:
     per-gate kernels execute (dense gates on >= 3 targets, measurements)."""
 
     def __init__(self, backend, queue, nqubits, dtype=None, tile_bits=None, run_bits=None,
-                 max_diag_bits=10):
+                 max_diag_bits=10, zero_state=False):
         self.backend = backend
+        self.zero_state = bool(zero_state)   # valid on |0...0> only (SWAP gates relabelled away)
         self.nqubits = int(nqubits)
         self.dtype = str(dtype or backend.dtype)
         self.tile_bits = min(int(tile_bits or DEFAULT_TILE_BITS[self.dtype]), MAX_TILE_BITS[self.dtype])
@@ -346,7 +375,7 @@ class Program:
             return
         pending = []
         for seg in plan_queue(queue, self.nqubits, backend.custom_matrices, self.tile_bits,
-                              self.run_bits, self.max_diag_bits, self.dtype):
+                              self.run_bits, self.max_diag_bits, self.dtype, self.zero_state):
             if seg[0] == "raw":
                 self._flush(pending)
                 pending = []

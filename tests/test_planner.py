@@ -146,3 +146,49 @@ def test_local_gates_of_the_distributed_layer_lower_like_their_originals():
         for x, y in zip(a, b):
             assert x.targets == y.targets and x.controls == y.controls
             np.testing.assert_allclose(np.asarray(x.data), np.asarray(y.data), atol=1e-15)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_swaps_are_relabelled_away_from_the_zero_state(seed):
+    """zero_state plans contain no SWAP and give the same final state from |0...0>."""
+    n = 9
+    rng = np.random.default_rng(seed)
+    glist = []
+    for g in random_circuit_gates(n, 50, seed + 100):
+        if len(g.target_qubits) > 2:           # raw gates switch the optimisation off (tested below)
+            continue
+        glist.append(g)
+        if rng.random() < 0.25:
+            a, b = rng.choice(n, size=2, replace=False)
+            glist.append(gates.SWAP(int(a), int(b)))
+    glist.append(gates.SWAP(0, n - 1))
+    plan = planner.plan_queue(glist, n, MATS, 7, 3, zero_state=True)
+    for op in _ops(plan):
+        assert not (op.kind == "dense" and len(op.targets) == 2 and not op.controls
+                    and np.array_equal(np.asarray(op.data).reshape(4, 4), planner._SWAP_MATRIX))
+    st = np.zeros(1 << n, dtype=np.complex128)
+    st[0] = 1
+    got = plan_interp.run_plan(st.copy(), plan, n, _raw(n))
+    ref = R.reference_run(st, glist, n)
+    np.testing.assert_allclose(got, ref, rtol=0, atol=1e-12)
+
+
+def test_qft_from_zero_state_needs_no_swap_passes():
+    n = 33
+    q = circuits.qft(n).queue
+    with_swaps = planner.plan_queue(q, n, MATS, 11, 5)
+    without = planner.plan_queue(q, n, MATS, 11, 5, zero_state=True)
+    assert len(without) <= len(with_swaps) - 3
+    small = circuits.qft(10).queue
+    st = np.zeros(1 << 10, dtype=np.complex128)
+    st[0] = 1
+    got = plan_interp.run_plan(st, planner.plan_queue(small, 10, MATS, 6, 3, zero_state=True), 10, _raw(10))
+    np.testing.assert_allclose(got, np.full(1 << 10, 2.0 ** -5), rtol=0, atol=1e-14)
+
+
+def test_raw_gates_keep_the_swaps():
+    n = 8
+    u = np.linalg.qr(np.random.default_rng(1).standard_normal((8, 8)))[0]
+    glist = [gates.H(0), gates.Unitary(u, 0, 3, 5), gates.SWAP(1, 2)]
+    plan = planner.plan_queue(glist, n, MATS, 6, 3, zero_state=True)
+    assert any(op.kind == "dense" and len(op.targets) == 2 for op in _ops(plan))

@@ -125,3 +125,42 @@ def test_program_rejects_dense_target_outside_the_registers():
     rounds[0]["reg_bits"][:4] = [0, 1, 2, 8]
     rc, _ = _create(b, 10, passes, rounds, ops, data)
     assert rc == _capi.QJ_ERR_INVALID and b"register bit is not a local bit" in b._lib.qj_last_error()
+
+
+@pytest.mark.parametrize("dtype", ["complex128", "complex64"])
+@pytest.mark.parametrize("seed", range(3))
+def test_zero_state_program_relabels_swaps(seed, dtype):
+    """Programs compiled for the |0...0> input drop the SWAP gates (planner.relabel_swaps_away):
+    same final state as gate by gate, through execute_circuit and through Program directly."""
+    from qibojit_b200.circuit import Circuit
+
+    b = backend()
+    n = 14
+    rng = np.random.default_rng(seed)
+    glist = []
+    for g in random_circuit_gates(n, 60, seed + 7):
+        if len(g.target_qubits) > 2:
+            continue
+        glist.append(g)
+        if rng.random() < 0.2:
+            a, c = rng.choice(n, size=2, replace=False)
+            glist.append(gates.SWAP(int(a), int(c)))
+    glist += [gates.SWAP(i, n - 1 - i) for i in range(n // 2)]
+    st = np.zeros(1 << n, dtype=dtype)
+    st[0] = 1
+    ref = R.reference_run(st.astype(np.complex128), glist, n)
+    got, _ = _run(b, glist, st, n, dtype, zero_state=True)
+    atol = ATOL[dtype] * 20 if dtype == "complex64" else 1e-12
+    np.testing.assert_allclose(got, ref, rtol=0, atol=atol)
+    c = Circuit(n)
+    c.add(glist)
+    b.set_dtype(dtype)
+    try:
+        out = b.to_numpy(b.execute_circuit(c))
+        np.testing.assert_allclose(out, ref, rtol=0, atol=atol)
+        # a given initial state keeps the swaps
+        rs = R.random_state(n, dtype, seed)
+        out = b.to_numpy(b.execute_circuit(c, initial_state=rs))
+        np.testing.assert_allclose(out, R.reference_run(rs, glist, n), rtol=0, atol=atol)
+    finally:
+        b.set_dtype("complex128")

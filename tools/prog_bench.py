@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--run-bits", type=int, default=0)
     ap.add_argument("--diag-bits", type=int, default=10)
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--keep-swaps", action="store_true", help="do not compile for the |0...0> input (SWAP gates stay)")
     ap.add_argument("--out", default="")
     args = ap.parse_args()
 
@@ -42,7 +43,8 @@ def main():
     c = build(n)
     t0 = time.perf_counter()
     prog = planner.Program(b, c.queue, n, dtype=args.dtype, tile_bits=args.tile_bits or None,
-                           run_bits=args.run_bits or None, max_diag_bits=args.diag_bits)
+                           run_bits=args.run_bits or None, max_diag_bits=args.diag_bits,
+                           zero_state=not args.keep_swaps)
     t_plan = time.perf_counter() - t0
     stats = prog.stats()
     state = b.zero_state(n)
