@@ -19,7 +19,6 @@ cannot be installed offline) and prints the same JSON line.
 """
 
 import argparse
-import ctypes
 import json
 import os
 import subprocess

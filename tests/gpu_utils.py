@@ -2,7 +2,6 @@
 
 import functools
 
-import numpy as np
 import pytest
 
 from oracle import oracle as O

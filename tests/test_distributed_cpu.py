@@ -7,7 +7,6 @@ import sys
 
 import numpy as np
 import pytest
-import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
@@ -15,7 +14,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _reference_state(circuit, dtype):
-    from oracle import oracle as O
     from qibojit_b200 import fusion
     from qibojit_b200.matrices import CustomMatrices
     from tests import refdispatch as R
