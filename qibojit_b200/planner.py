@@ -54,7 +54,9 @@ DIAGONAL_GATES = frozenset({
 # complex128: 32 KiB tiles, four 128-thread CTAs per SM in different phases (measured 4-6 % faster
 # than two 64 KiB tiles although a pass covers one qubit less); complex64: 64 KiB tiles
 DEFAULT_TILE_BITS = {"complex128": 11, "complex64": 13}
-DEFAULT_RUN_BITS = {"complex128": 5, "complex64": 6}
+# contiguous run of a tile in global memory: 256 bytes (whole sectors; measured as fast as 512-byte
+# runs and it leaves one more tile bit for arbitrary high qubits: fewer passes)
+DEFAULT_RUN_BITS = {"complex128": 4, "complex64": 5}
 MAX_TILE_BITS = {"complex128": 12, "complex64": 13}   # 64 KiB tiles, two resident CTAs per SM
 REG_BITS = {"complex128": 4, "complex64": 5}          # register bits per round (complex64: bit 0 + 4)
 MAX_HI_BITS = 8
