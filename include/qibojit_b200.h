@@ -227,6 +227,22 @@ int qj_program_run_launch(qj_handle *h, const qj_program *p, void *state, int la
 int qj_program_stats(const qj_program *p, int64_t *nlaunches, int64_t *nrounds, int64_t *nmops);
 int qj_program_destroy(qj_handle *h, qj_program *p);
 
+/* Inspection (CPU tests of the host-side encoder; no device needed): the encoded image of the
+ * same arguments -- program units (16 bytes each), phase tables / per-thread factors, and per
+ * launch QJ_LAUNCH_INFO_FIELDS int64 values {tile bits, run bits, high bits, tiles, first unit,
+ * units, per-tile factors, shared-memory bytes, high bit positions[8]}.
+ * tests/pass_emulator.py interprets it.                                                       */
+#define QJ_LAUNCH_INFO_FIELDS 16
+typedef struct qj_program_image qj_program_image;
+int qj_program_encode(int dtype, int nqubits, const qj_pass_desc *passes, int npasses,
+                      const qj_round_desc *rounds, int64_t nrounds, const qj_op_desc *ops,
+                      int64_t nops, const void *data, int64_t ndata, qj_program_image **out);
+int qj_program_image_sizes(const qj_program_image *img, int64_t *nlaunches, int64_t *blob_bytes,
+                           int64_t *table_bytes);
+int qj_program_image_read(const qj_program_image *img, void *blob_out, void *tables_out,
+                          int64_t *launch_info);
+int qj_program_image_destroy(qj_program_image *img);
+
 #ifdef __cplusplus
 }
 #endif

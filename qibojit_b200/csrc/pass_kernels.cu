@@ -920,11 +920,21 @@ struct qj_program {
 
 using namespace qj;
 
-extern "C" int qj_program_create(qj_handle *h, int dtype, int nqubits, const qj_pass_desc *passes,
-                                 int npasses, const qj_round_desc *rounds_in, int64_t nrounds_in,
-                                 const qj_op_desc *ops, int64_t nops, const void *data, int64_t ndata,
-                                 qj_program **out) {
-    QJ_REQUIRE(h && out && (passes || npasses == 0), "null argument");
+// host image of an encoded program (qj_program_encode: inspection / CPU tests of the encoder)
+struct qj_program_image {
+    int dtype = 0, nqubits = 0;
+    std::vector<Unit> blob;
+    std::vector<unsigned char> tables;
+    std::vector<qj_program::Launch> launches;
+};
+
+// Encodes the passes; uploads them into a qj_program (h, out) or, when `image` is given, hands the
+// host image back without touching a device.
+static int program_build(qj_handle *h, int dtype, int nqubits, const qj_pass_desc *passes,
+                         int npasses, const qj_round_desc *rounds_in, int64_t nrounds_in,
+                         const qj_op_desc *ops, int64_t nops, const void *data, int64_t ndata,
+                         qj_program **out, qj_program_image *image) {
+    QJ_REQUIRE(((h && out) || image) && (passes || npasses == 0), "null argument");
     QJ_REQUIRE(dtype == QJ_C64 || dtype == QJ_C128, "dtype must be QJ_C64 or QJ_C128");
     QJ_REQUIRE(nqubits >= kMinTileBits && nqubits <= QJ_MAX_QUBITS, "tile programs need 6 <= nqubits <= QJ_MAX_QUBITS");
     QJ_REQUIRE(npasses >= 0 && nrounds_in >= 0 && nops >= 0 && ndata >= 0, "negative count");
@@ -1497,6 +1507,15 @@ extern "C" int qj_program_create(qj_handle *h, int dtype, int nqubits, const qj_
         close_launch();
     }
 
+    if (image) {
+        image->dtype = dtype;
+        image->nqubits = nqubits;
+        image->blob = blob_all;
+        image->tables = enc.tables;
+        image->launches = prog->launches;
+        delete prog;
+        return QJ_OK;
+    }
     cudaSetDevice(h->device);
     auto upload = [&](void **dst, const void *src, size_t bytes) -> cudaError_t {
         if (bytes == 0) bytes = 16;   // never hand a null table pointer to the kernel
@@ -1512,6 +1531,60 @@ extern "C" int qj_program_create(qj_handle *h, int dtype, int nqubits, const qj_
         return fail(QJ_ERR_CUDA, std::string("program upload: ") + cudaGetErrorString(e));
     }
     *out = prog;
+    return QJ_OK;
+}
+
+extern "C" int qj_program_create(qj_handle *h, int dtype, int nqubits, const qj_pass_desc *passes,
+                                 int npasses, const qj_round_desc *rounds_in, int64_t nrounds_in,
+                                 const qj_op_desc *ops, int64_t nops, const void *data, int64_t ndata,
+                                 qj_program **out) {
+    QJ_REQUIRE(h && out, "null argument");
+    return program_build(h, dtype, nqubits, passes, npasses, rounds_in, nrounds_in, ops, nops, data, ndata, out, nullptr);
+}
+
+extern "C" int qj_program_encode(int dtype, int nqubits, const qj_pass_desc *passes, int npasses,
+                                 const qj_round_desc *rounds_in, int64_t nrounds_in, const qj_op_desc *ops,
+                                 int64_t nops, const void *data, int64_t ndata, qj_program_image **out) {
+    QJ_REQUIRE(out != nullptr, "null argument");
+    auto *img = new qj_program_image();
+    const int rc = program_build(nullptr, dtype, nqubits, passes, npasses, rounds_in, nrounds_in, ops, nops, data,
+                                 ndata, nullptr, img);
+    if (rc != QJ_OK) {
+        delete img;
+        return rc;
+    }
+    *out = img;
+    return QJ_OK;
+}
+
+extern "C" int qj_program_image_sizes(const qj_program_image *img, int64_t *nlaunches, int64_t *blob_bytes,
+                                      int64_t *table_bytes) {
+    QJ_REQUIRE(img != nullptr, "null image");
+    if (nlaunches) *nlaunches = int64_t(img->launches.size());
+    if (blob_bytes) *blob_bytes = int64_t(img->blob.size()) * 16;
+    if (table_bytes) *table_bytes = int64_t(img->tables.size());
+    return QJ_OK;
+}
+
+extern "C" int qj_program_image_read(const qj_program_image *img, void *blob_out, void *tables_out,
+                                     int64_t *launch_info) {
+    QJ_REQUIRE(img != nullptr, "null image");
+    if (blob_out && !img->blob.empty()) memcpy(blob_out, img->blob.data(), img->blob.size() * 16);
+    if (tables_out && !img->tables.empty()) memcpy(tables_out, img->tables.data(), img->tables.size());
+    if (launch_info) {
+        for (size_t i = 0; i < img->launches.size(); i++) {
+            const qj_program::Launch &L = img->launches[i];
+            int64_t *o = launch_info + QJ_LAUNCH_INFO_FIELDS * i;
+            o[0] = L.geom.T; o[1] = L.geom.r; o[2] = L.geom.nh; o[3] = L.geom.ntiles;
+            o[4] = L.blob_off; o[5] = L.geom.blob_units; o[6] = L.geom.nH; o[7] = int64_t(L.smem);
+            for (int b = 0; b < kMaxHiBits; b++) o[8 + b] = L.geom.hibit[b];
+        }
+    }
+    return QJ_OK;
+}
+
+extern "C" int qj_program_image_destroy(qj_program_image *img) {
+    delete img;
     return QJ_OK;
 }
 
