@@ -327,6 +327,40 @@ def relabel_swaps_away(ops, nqubits):
     return out
 
 
+def fuse_one_qubit_runs(ops):
+    """Multiply uncontrolled one-target gates that follow each other on the same bit (nothing in
+    between touches that bit) into one 2x2: H then RX on a qubit costs one register update instead
+    of two.  A one-bit uncontrolled phase next to such a gate is folded in as well."""
+    out = []
+    last = {}          # index bit -> position in `out` of the last op that touches it
+
+    def as_matrix(op):
+        if op.kind == "dense" and len(op.targets) == 1 and not op.controls:
+            return np.asarray(op.data, dtype=np.complex128).reshape(2, 2)
+        if op.kind == "diag" and len(op.targets) == 1 and not op.controls:
+            return np.diag(np.asarray(op.data, dtype=np.complex128).reshape(2))
+        return None
+
+    for op in ops:
+        m = as_matrix(op)
+        if m is not None:
+            t = op.targets[0]
+            j = last.get(t)
+            if j is not None:
+                prev = as_matrix(out[j])
+                if prev is not None and out[j].targets[0] == t and (op.kind == "dense" or out[j].kind == "dense"):
+                    out[j] = PlanOp("dense", (t,), (), m @ prev)
+                    continue
+        if op.kind != "raw":
+            for b in op.bits:
+                last[b] = len(out)
+        else:
+            last = {b: len(out) for b in list(last)}   # a raw gate's qubits are not known here: it blocks every bit seen so far
+            last[-1] = len(out)
+        out.append(op)
+    return out
+
+
 def plan_queue(queue, nqubits, matrices, tile_bits, run_bits, max_diag_bits=10, dtype="complex128",
                zero_state=False):
     """Gate queue -> [('pass', local_bits, [(reg_bits, [PlanOp])]) | ('raw', gate)] (host logic).
@@ -336,6 +370,7 @@ def plan_queue(queue, nqubits, matrices, tile_bits, run_bits, max_diag_bits=10, 
         ops.extend(lower_gate(gate, nqubits, matrices))
     if zero_state:
         ops = relabel_swaps_away(ops, nqubits)
+    ops = fuse_one_qubit_runs(ops)
     nreg = REG_BITS[str(dtype)]
     fixed = (0,) if str(dtype) == "complex64" else ()
     mdb = min(max_diag_bits, _capi.QJ_MAX_DIAG_BITS)

@@ -192,3 +192,20 @@ def test_raw_gates_keep_the_swaps():
     glist = [gates.H(0), gates.Unitary(u, 0, 3, 5), gates.SWAP(1, 2)]
     plan = planner.plan_queue(glist, n, MATS, 6, 3, zero_state=True)
     assert any(op.kind == "dense" and len(op.targets) == 2 for op in _ops(plan))
+
+
+def test_adjacent_one_qubit_gates_are_fused():
+    n = 8
+    glist = [gates.H(0), gates.RX(0, 0.3), gates.RZ(0, 0.2), gates.CZ(0, 1), gates.H(0), gates.H(1), gates.T(1),
+             gates.RY(1, 0.4), gates.Z(2), gates.S(2)]
+    plan = planner.plan_queue(glist, n, MATS, 6, 3)
+    ops = _ops(plan)
+    dense = [op for op in ops if op.kind == "dense"]
+    assert len(dense) == 3                     # H.RX.RZ on qubit 0 | H on 0 after the CZ | H.T.RY on 1
+    st = R.random_state(n, "complex128", 2)
+    got = plan_interp.run_plan(st.copy(), plan, n, _raw(n))
+    np.testing.assert_allclose(got, R.reference_run(st, glist, n), rtol=0, atol=1e-13)
+    # phases alone stay phases (they merge into tables)
+    assert all(op.kind == "diag" for op in _ops(planner.plan_queue([gates.Z(2), gates.S(2), gates.T(2)], n, MATS, 6, 3)))
+    sup = circuits.supremacy(12, depth=4)
+    assert len(_ops(planner.plan_queue(sup.queue, 12, MATS, 8, 3))) <= len(sup.queue) - 12   # H + first-cycle gate
