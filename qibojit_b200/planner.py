@@ -122,6 +122,8 @@ def partition(ops, nqubits, tile_bits, run_bits):
     r = max(1, min(run_bits, T))
     if T - r > MAX_HI_BITS:
         r = T - MAX_HI_BITS
+    if T < nqubits:
+        r = min(r, T - 2)    # a two-target gate on two high qubits needs two arbitrary tile bits
     segments = []
     remaining = list(ops)
     while remaining:
@@ -155,6 +157,8 @@ def partition(ops, nqubits, tile_bits, run_bits):
                 blocked_t |= op.tset
                 blocked_d |= op.dset
                 rest.append(op)
+        if not taken:
+            raise RuntimeError("pass planner made no progress (tile too small for the next gate)")
         b = 0
         while len(local) < T:  # pad with the lowest free bits: longer contiguous runs
             if b not in local:

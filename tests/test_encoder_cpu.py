@@ -134,3 +134,40 @@ def test_default_geometry_images_fit_the_kernel_limits():
             assert kind == "image"
             for L in item.launches:
                 assert L["smem"] <= 200 << 10 and L["blob_units"] <= 2560 and L["nh"] <= 8
+
+
+def test_random_geometries_fuzz():
+    """150 random (n, dtype, tile, run, table size, circuit, zero-state) combinations through
+    planner + encoder + emulator (a longer run of the same loop found the r = T planner hang)."""
+    rng = np.random.default_rng(2024)
+    for _ in range(150):
+        n = int(rng.integers(6, 11))
+        dtype = ["complex128", "complex64"][int(rng.integers(0, 2))]
+        T = int(rng.integers(6, min(n, 12 if dtype == "complex128" else 13) + 1))
+        r = int(rng.integers(1, T + 1))
+        mdb = int(rng.integers(2, 13))
+        seed = int(rng.integers(0, 1 << 30))
+        zero = bool(rng.integers(0, 2))
+        glist = random_circuit_gates(n, int(rng.integers(5, 50)), seed)
+        if rng.random() < 0.5:
+            glist = [g for g in glist if len(g.target_qubits) <= 2]
+        if rng.random() < 0.5:
+            a, b = (int(v) for v in rng.choice(n, size=2, replace=False))
+            glist.insert(int(rng.integers(0, len(glist) + 1)), gates.SWAP(a, b))
+        st = np.zeros(1 << n, dtype=np.complex128)
+        st[0] = 1
+        if not zero:
+            st = R.random_state(n, "complex128", seed % 1000)
+        got, _ = _run(glist, st, n, dtype, tile_bits=T, run_bits=r, max_diag_bits=mdb, zero_state=zero)
+        np.testing.assert_allclose(got, R.reference_run(st, glist, n), rtol=0,
+                                   atol=1e-11 if dtype == "complex128" else 2e-4,
+                                   err_msg=str(dict(n=n, dtype=dtype, T=T, r=r, mdb=mdb, seed=seed, zero=zero)))
+
+
+def test_tile_without_free_high_bits_does_not_hang():
+    """run_bits == tile_bits < nqubits used to loop forever in planner.partition."""
+    glist = random_circuit_gates(8, 14, 334108495)
+    st = np.zeros(1 << 8, dtype=np.complex128)
+    st[0] = 1
+    got, _ = _run(glist, st, 8, "complex128", tile_bits=6, run_bits=6, max_diag_bits=3, zero_state=True)
+    np.testing.assert_allclose(got, R.reference_run(st, glist, 8), rtol=0, atol=1e-12)
