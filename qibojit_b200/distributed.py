@@ -475,25 +475,33 @@ class DistributedState:
                                 and len(uses[q]) > upos[q]), key=lambda q: uses[q][upos[q]])
                 spare = len(finished) - len(wanted)
                 wanted.extend(later[:max(0, spare)])
-            pairs, taken = [], set()
-            for q in wanted:
-                best, best_key = None, None
-                for v in range(self.nqubits):
-                    if not self.is_local(v) or v in keep or v in taken:
-                        continue
-                    if self.dtype == "complex64" and self.bit_of[v] == 0:
-                        continue  # 16-byte exchange granularity
-                    left = len(uses[v]) - upos[v]
-                    nxt_use = uses[v][upos[v]] if left else len(gates)
-                    key = (left, -nxt_use, -self.bit_of[v])   # prefer the top bit: contiguous halves
-                    if best is None or key < best_key:
-                        best, best_key = v, key
-                if best is None:
-                    if pairs:
-                        break           # fewer victims than wanted qubits: the rest waits
-                    raise RuntimeError("no local qubit available to swap with")
-                taken.add(best)
-                pairs.append((q, best))
+            def choose(wanted, keep):
+                pairs, taken = [], set()
+                for q in wanted:
+                    best, best_key = None, None
+                    for v in range(self.nqubits):
+                        if not self.is_local(v) or v in keep or v in taken:
+                            continue
+                        if self.dtype == "complex64" and self.bit_of[v] == 0:
+                            continue  # 16-byte exchange granularity
+                        left = len(uses[v]) - upos[v]
+                        nxt_use = uses[v][upos[v]] if left else len(gates)
+                        key = (left, -nxt_use, -self.bit_of[v])   # prefer the top bit: contiguous halves
+                        if best is None or key < best_key:
+                            best, best_key = v, key
+                    if best is None:
+                        break               # fewer victims than wanted qubits: the rest waits
+                    taken.add(best)
+                    pairs.append((q, best))
+                return pairs
+
+            pairs = choose(wanted, keep)
+            if not pairs:
+                # the blocked gates together pin every local qubit: serve the earliest one alone
+                first = needs[min(blocked)]
+                pairs = choose([q for q in first if not self.is_local(q)], set(first))
+            if not pairs:
+                raise RuntimeError("no local qubit available to swap with")
             self._plan_multi_exchange(steps, pairs)
             for j in blocked:
                 heapq.heappush(ready, j)

@@ -179,3 +179,25 @@ def test_dag_schedule_needs_few_exchanges():
     assert count(circuits.supremacy(36), 36, 8, "complex64") == (1, 0.875)
     assert count(circuits.qft(36), 36, 8, "complex64") == (1, 0.875)
     assert count(circuits.supremacy(36), 36, 8, "complex64", batch_exchanges=False) == (3, 1.5)
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_distributed_plans_fuzz_in_one_process(world):
+    """Random circuits (controls / diagonals / SWAPs on global qubits included) through every
+    rank's plan, run in lockstep in one process (tests/virtual_ranks.py), in the three schedules."""
+    from tests import refdispatch as R
+    from tests.circuits_random import random_circuit_gates
+    from tests.virtual_ranks import run_virtual
+
+    rng = np.random.default_rng(world)
+    for case in range(12):
+        n = int(rng.integers(world.bit_length() + 3, 9))
+        dtype = ["complex128", "complex64"][case % 2]
+        glist = [g for g in random_circuit_gates(n, int(rng.integers(10, 60)), int(rng.integers(0, 1 << 30)))]
+        st = np.zeros(1 << n, dtype=np.complex128)
+        st[0] = 1
+        ref = R.reference_run(st, glist, n)
+        for kw in ({}, {"batch_exchanges": False}, {"reorder": False}):
+            got, _ = run_virtual(glist, n, world, dtype, **kw)
+            np.testing.assert_allclose(got, ref, rtol=0, atol=1e-12 if dtype == "complex128" else 2e-5,
+                                       err_msg=f"case {case} n={n} {dtype} {kw}")
