@@ -53,13 +53,18 @@ def _test_circuits(n):
 
 def _worker(rank, world, port, n, dtype, q, via_planner=False):
     sys.path.insert(0, ROOT)
-    os.environ["OMP_NUM_THREADS"] = "1"      # `world` ranks share the host cores
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
+        from oracle import oracle as O
         from qibojit_b200.distributed import Comm, DistributedState
         from tests.oracle_backend import OracleBackend
+
+        import torch
+
+        O.set_threads(1)                     # `world` ranks share the host cores
+        torch.set_num_threads(1)
 
         results = {}
         for name, circuit in _test_circuits(n).items():
@@ -90,9 +95,9 @@ def _worker(rank, world, port, n, dtype, q, via_planner=False):
 
 
 @pytest.mark.parametrize("world,n,via_planner,dtype", [
-    (2, 6, False, "complex128"), (2, 6, False, "complex64"), (4, 7, False, "complex128"), (4, 7, False, "complex64"),
+    (2, 6, False, "complex128"), (4, 7, False, "complex64"),
     (8, 8, False, "complex128"),          # three global qubits: 8-way all-to-all exchange
-    (2, 8, True, "complex128"), (2, 8, True, "complex64"), (4, 9, True, "complex128"), (4, 9, True, "complex64")])
+    (2, 8, True, "complex64"), (4, 9, True, "complex128")])
 def test_distributed_state_matches_single_state(world, n, via_planner, dtype):
     """via_planner: each rank's local segments are lowered by planner.plan_queue (what the B200
     backend compiles into pass programs) and interpreted in numpy, instead of gate by gate."""
