@@ -171,3 +171,26 @@ def test_tile_without_free_high_bits_does_not_hang():
     st[0] = 1
     got, _ = _run(glist, st, 8, "complex128", tile_bits=6, run_bits=6, max_diag_bits=3, zero_state=True)
     np.testing.assert_allclose(got, R.reference_run(st, glist, 8), rtol=0, atol=1e-12)
+
+
+def test_whole_gate_table_fuzz():
+    """Every gate class of qibojit_b200.gates (with extra controls) through planner + encoder +
+    emulator, and through the distributed planner with all ranks in one process."""
+    from tests.circuits_random import random_gate_any
+    from tests.virtual_ranks import run_virtual
+
+    rng = np.random.default_rng(77)
+    for case in range(80):
+        n = int(rng.integers(7, 10))
+        dtype = ["complex128", "complex64"][case % 2]
+        glist = [random_gate_any(n, rng) for _ in range(int(rng.integers(5, 50)))]
+        st = np.zeros(1 << n, dtype=np.complex128)
+        st[0] = 1
+        ref = R.reference_run(st, glist, n)
+        atol = 1e-11 if dtype == "complex128" else 2e-4
+        T = int(rng.integers(6, n + 1))
+        got, _ = _run(glist, st, n, dtype, tile_bits=T, run_bits=int(rng.integers(1, T + 1)),
+                      max_diag_bits=int(rng.integers(2, 13)), zero_state=bool(case % 3 == 0))
+        np.testing.assert_allclose(got, ref, rtol=0, atol=atol, err_msg=f"case {case}")
+        got, _ = run_virtual(glist, n, [2, 4, 8][case % 3], dtype)
+        np.testing.assert_allclose(got, ref, rtol=0, atol=atol, err_msg=f"case {case} (distributed)")
