@@ -208,7 +208,7 @@ def run_reference(args):
         "impl": "reference", "metric": "gates_per_second", "value": value, "unit": "gates/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * (time.perf_counter() - t0) / max(1, args.steps + args.warmup),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64" if dtype == "complex128" else "f32",
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64" if dtype == "complex128" else "f32",
         "data": "synthetic",
         "config": {"workload": f"{args.workload}-{nqubits}-{dtype}", "fusion_max_qubits": min(2, cfg["fuse"]),
                    "note": "CPU port (oracle/qj_oracle.c, C+OpenMP) of the reference numba kernels"},
@@ -398,7 +398,7 @@ def run_ours(args):
     line = {
         "metric": "gates_per_second", "value": value, "unit": "gates/s", "n_gpus": 1,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64" if dtype == "complex128" else "f32", "data": "synthetic",
         "config": {"workload": f"{args.workload}-{nqubits}-{dtype}", "circuit_gates": ngates,
                    "execution": "multi-gate tile passes (planner.Program compiled for the |0...0> input: SWAP gates are relabellings)",
