@@ -686,11 +686,38 @@ class B200Backend(_QiboBackend):
             state = gate.apply(self, state, nqubits)
         return state
 
+    @staticmethod
+    def circuit_fingerprint(queue):
+        """Hashable summary of a gate queue -- classes, qubits AND parameter values -- so that a
+        cached program is not reused after `circuit.set_parameters(...)` (the matrices are baked
+        into the program image)."""
+        def param(p):
+            if hasattr(p, "tobytes"):
+                a = np.ascontiguousarray(p)
+                return (a.shape, str(a.dtype), hash(a.tobytes()))
+            if isinstance(p, (list, tuple)):
+                return tuple(param(x) for x in p)
+            try:
+                hash(p)
+                return p
+            except TypeError:
+                return repr(p)
+
+        out = []
+        for g in queue:
+            item = (g.__class__.__name__, tuple(g.target_qubits), tuple(g.control_qubits),
+                    tuple(param(x) for x in getattr(g, "parameters", ())))
+            if hasattr(g, "gates"):               # FusedGate
+                item += (B200Backend.circuit_fingerprint(g.gates),)
+            out.append(item)
+        return hash(tuple(out))
+
     def compile_circuit(self, circuit, **options):
         """Compile (and cache on the circuit object) the multi-gate pass program of `circuit`."""
         from ..planner import Program
 
-        key = (self.dtype, self._device_index, len(circuit.queue), tuple(sorted(options.items())))
+        key = (self.dtype, self._device_index, len(circuit.queue), self.circuit_fingerprint(circuit.queue),
+               tuple(sorted(options.items())))
         cache = circuit.__dict__.setdefault("_qj_programs", {})
         prog = cache.get(key)
         if prog is None:

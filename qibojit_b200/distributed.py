@@ -607,7 +607,8 @@ def execute_distributed_circuit(backend, circuit, initial_state=None, nshots=Non
     if initial_state is not None:
         raise TypeError("distributed execution starts from |0...0>; initial states are not supported")
     state = DistributedState(backend, circuit.nqubits, comm=comm)
-    key = ("dist", state.rank, state.comm.world, backend.dtype)
+    fingerprint = getattr(backend, "circuit_fingerprint", lambda q: len(q))(circuit.queue)
+    key = ("dist", state.rank, state.comm.world, backend.dtype, len(circuit.queue), fingerprint)
     cache = circuit.__dict__.setdefault("_qj_programs", {})
     steps = cache.get(key)
     if steps is None:

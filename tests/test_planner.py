@@ -209,3 +209,22 @@ def test_adjacent_one_qubit_gates_are_fused():
     assert all(op.kind == "diag" for op in _ops(planner.plan_queue([gates.Z(2), gates.S(2), gates.T(2)], n, MATS, 6, 3)))
     sup = circuits.supremacy(12, depth=4)
     assert len(_ops(planner.plan_queue(sup.queue, 12, MATS, 8, 3))) <= len(sup.queue) - 12   # H + first-cycle gate
+
+
+def test_program_cache_key_follows_gate_parameters():
+    """B200Backend.compile_circuit caches the program on the circuit object: the key must change
+    when a gate parameter (or a Unitary's matrix) changes, because matrices are baked into the image."""
+    from qibojit_b200.backends.b200 import B200Backend
+
+    fp = B200Backend.circuit_fingerprint
+    a = [gates.RY(0, 0.3), gates.CZ(0, 1), gates.Unitary(np.eye(2), 2)]
+    b = [gates.RY(0, 0.3), gates.CZ(0, 1), gates.Unitary(np.eye(2), 2)]
+    assert fp(a) == fp(b)
+    b[0].parameters = (0.31,)
+    assert fp(a) != fp(b)
+    c = [gates.RY(0, 0.3), gates.CZ(0, 1), gates.Unitary(np.array([[0, 1], [1, 0]]), 2)]
+    assert fp(a) != fp(c)
+    assert fp(a) != fp([gates.RY(0, 0.3), gates.CZ(1, 0), gates.Unitary(np.eye(2), 2)])
+    fused = circuits.variational(6).fuse(2)
+    assert fp(fused.queue) == fp(circuits.variational(6).fuse(2).queue)
+    assert fp(fused.queue) != fp(circuits.variational(6, seed=5).fuse(2).queue)
