@@ -388,7 +388,7 @@ def run_ours(args):
         if i:
             e2e_times.append(time.perf_counter() - t0)
         d2h = host.nbytes
-        h2d = sum(p.upload_bytes for p in circuit.__dict__.get("_qj_programs", {}).values())
+        h2d = sum(entry[1].upload_bytes for entry in circuit.__dict__.get("_qj_programs", {}).values())
         del out, probs      # the block goes back to torch's caching allocator and is reused by the next step
     e2e_value = ngates / float(np.mean(e2e_times))
     assert abs(host.sum() - 1.0) < (1e-6 if dtype == 'complex128' else 1e-3), host.sum()

@@ -716,14 +716,17 @@ class B200Backend(_QiboBackend):
         """Compile (and cache on the circuit object) the multi-gate pass program of `circuit`."""
         from ..planner import Program
 
-        key = (self.dtype, self._device_index, len(circuit.queue), self.circuit_fingerprint(circuit.queue),
-               tuple(sorted(options.items())))
+        key = (self.dtype, self._device_index, tuple(sorted(options.items())))
+        fingerprint = (len(circuit.queue), self.circuit_fingerprint(circuit.queue))
         cache = circuit.__dict__.setdefault("_qj_programs", {})
-        prog = cache.get(key)
-        if prog is None:
-            prog = Program(self, circuit.queue, circuit.nqubits, dtype=self.dtype, **options)
-            cache[key] = prog
-        return prog
+        entry = cache.get(key)
+        if entry is not None and entry[0] != fingerprint:
+            entry[1].close()          # re-parametrised circuit: one program per key, no pile-up
+            entry = None
+        if entry is None:
+            entry = (fingerprint, Program(self, circuit.queue, circuit.nqubits, dtype=self.dtype, **options))
+            cache[key] = entry
+        return entry[1]
 
     def execute_distributed_circuit(self, circuit, initial_state=None, nshots=None):
         from ..distributed import execute_distributed_circuit

@@ -607,11 +607,12 @@ def execute_distributed_circuit(backend, circuit, initial_state=None, nshots=Non
     if initial_state is not None:
         raise TypeError("distributed execution starts from |0...0>; initial states are not supported")
     state = DistributedState(backend, circuit.nqubits, comm=comm)
-    fingerprint = getattr(backend, "circuit_fingerprint", lambda q: len(q))(circuit.queue)
-    key = ("dist", state.rank, state.comm.world, backend.dtype, len(circuit.queue), fingerprint)
+    fingerprint = (len(circuit.queue), getattr(backend, "circuit_fingerprint", len)(circuit.queue))
+    key = ("dist", state.rank, state.comm.world, backend.dtype)
     cache = circuit.__dict__.setdefault("_qj_programs", {})
-    steps = cache.get(key)
-    if steps is None:
-        steps = cache[key] = state.plan(circuit.queue)
+    entry = cache.get(key)
+    if entry is None or entry[0] != fingerprint:     # (an outdated plan is dropped with its programs)
+        entry = cache[key] = (fingerprint, state.plan(circuit.queue))
+    steps = entry[1]
     state.run(steps)
     return state

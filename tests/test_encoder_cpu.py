@@ -194,3 +194,22 @@ def test_whole_gate_table_fuzz():
         np.testing.assert_allclose(got, ref, rtol=0, atol=atol, err_msg=f"case {case}")
         got, _ = run_virtual(glist, n, [2, 4, 8][case % 3], dtype)
         np.testing.assert_allclose(got, ref, rtol=0, atol=atol, err_msg=f"case {case} (distributed)")
+
+
+def test_compile_circuit_cache_is_replaced_when_parameters_change():
+    """B200Backend.compile_circuit on a device-free stand-in: same parameters -> the cached program,
+    new parameters -> a new program and the old one closed (no pile-up in a variational loop)."""
+    from qibojit_b200.backends.b200 import B200Backend
+
+    b = E.EncoderBackend("complex128")
+    b._device_index = 0
+    b.circuit_fingerprint = B200Backend.circuit_fingerprint
+    c = circuits.variational(8)
+    p1 = B200Backend.compile_circuit(b, c, zero_state=True)
+    assert B200Backend.compile_circuit(b, c, zero_state=True) is p1
+    p0 = B200Backend.compile_circuit(b, c)                       # other options: its own entry
+    assert p0 is not p1 and len(c.__dict__["_qj_programs"]) == 2
+    c.queue[0].parameters = (0.123,)
+    p2 = B200Backend.compile_circuit(b, c, zero_state=True)
+    assert p2 is not p1 and p1.segments == [] and len(c.__dict__["_qj_programs"]) == 2
+    assert B200Backend.compile_circuit(b, c, zero_state=True) is p2
