@@ -79,6 +79,8 @@ enum {
     C_PERM2 = 18,     // + pair index (SWAP)
     C_PHASE = 28,     // product of per-thread table look-ups, one complex multiply of the selected elements
     C_DIAGN = 29,     // general: one look-up per element
+    C_DENSE2R = 30,   // + pair index: REAL 4x4 (16 scalars): half the multiply-adds of the complex one
+    C_DIAGF = 40,     // fused diagonal: per-thread, per-element factors G[unit][tid] (x per-tile factors)
 };
 
 // element selection of a C_PHASE op (which of a thread's register amplitudes the phase multiplies)
@@ -97,11 +99,15 @@ struct PassGeom {
     int64_t ntiles;
     int blob_units;        // program image, 16-byte units
     int nH;                // per-tile phase factors (outer-only parts of the phase groups)
+    int nF;                // fused diagonals with an outer part (2^J per-tile, per-element factors each)
 };
 
 // ---- program image (16-byte units) -------------------------------------------------------------
 // unit 0            : {nrounds, nouter, off_rounds, off_outer}
-// unit 1            : {nH, off_H, 0, 0}
+// unit 1            : {nH, off_H, nF, off_F}
+// F region          : nF directory units {first slice unit (relative to off_F), nslices, 0, 0}, then the
+//                     slices {element mask, table, oslot, 0}: per-tile factor of element e of fused
+//                     diagonal f = product over its slices whose mask holds e of table[outer index]
 // H entries, 4 units: {ntab, 0, 0, 0} {table, oslot, table, oslot} x 3   (product of <= 6 outer-indexed look-ups)
 // rounds, 3 units   : {first_unit, nops, vd0 | vd1 << 16, vd2 | vd3 << 16}
 //                     {td[0..7] as uint16}  {tpos[0..7] as uint8, 0, 0}
@@ -318,6 +324,56 @@ __device__ __forceinline__ void op_dense2(Cx<T> (&x)[Lay<T>::N], const uint4 *pa
     }
 }
 
+// two-target gate with a REAL matrix (RY RY CZ RY RY on a pair, products of Hadamards and CZ, ...):
+// re and im parts transform separately, 8 multiply-adds per amplitude instead of 16
+template <typename T, int A, int B>
+__device__ __forceinline__ void dense2r_group(Cx<T> (&x)[Lay<T>::N], const uint4 *pay, int e0) {
+    Cx<T> s[4], y[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) s[j] = x[e0 | ((j & 1) << A) | ((j >> 1) << B)];
+    if constexpr (sizeof(T) == 4) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            float g[4];                                   // row i
+            load_units<1>(pay + i, g);
+            u64 acc = f2_mul(f2_splat(g[0]), f2_of(s[0]));
+#pragma unroll
+            for (int j = 1; j < 4; j++) acc = f2_fma(f2_splat(g[j]), f2_of(s[j]), acc);
+            f2_store(y[i], acc);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            T g[4];
+            load_units<2>(pay + 2 * i, g);
+            T ar = g[0] * s[0].re, ai = g[0] * s[0].im;
+#pragma unroll
+            for (int j = 1; j < 4; j++) { ar = fma(g[j], s[j].re, ar); ai = fma(g[j], s[j].im, ai); }
+            y[i].re = ar; y[i].im = ai;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) x[e0 | ((i & 1) << A) | ((i >> 1) << B)] = y[i];
+}
+
+template <typename T, int A, int B>
+__device__ __forceinline__ void op_dense2r(Cx<T> (&x)[Lay<T>::N], const uint4 *pay, uint32_t emask) {
+    constexpr int N = Lay<T>::N;
+    if constexpr (B < Lay<T>::J) {
+        if (emask == (N == 32 ? 0xffffffffu : 0xffffu)) {
+#pragma unroll
+            for (int p = 0; p < N / 4; p++) dense2r_group<T, A, B>(x, pay, insert0(insert0(p, A), B));
+        } else {
+#pragma unroll
+            for (int p = 0; p < N / 4; p++) {
+                const int e0 = insert0(insert0(p, A), B);
+                if (!((emask >> e0) & 1u)) continue;
+                dense2r_group<T, A, B>(x, pay, e0);
+            }
+        }
+    }
+}
+
 template <typename T, int A>
 __device__ __forceinline__ void op_perm1(Cx<T> (&x)[Lay<T>::N], uint32_t emask) {
     constexpr int N = Lay<T>::N;
@@ -436,6 +492,62 @@ __device__ __forceinline__ Cx<float> ldg_cx(const Cx<float> *p) {
     return c;
 }
 
+__device__ __forceinline__ float4 ldg_f4(const void *p) {
+    float4 c;
+    asm("ld.global.nc.L1::evict_last.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(c.x), "=f"(c.y), "=f"(c.z), "=f"(c.w) : "l"(p));
+    return c;
+}
+
+template <typename T>
+__device__ __forceinline__ Cx<T> cx_mul(const Cx<T> &a, const Cx<T> &b) {
+    Cx<T> o;
+    o.re = fma(a.re, b.re, -(a.im * b.im));
+    o.im = fma(a.re, b.im, a.im * b.re);
+    return o;
+}
+
+// Fused diagonal: every diagonal gate waiting at this point of the round whose other bits are all
+// inside the tile (-> G, one host-made factor per 16-byte unit and thread, laid out [unit][thread]:
+// coalesced, L1/L2 resident) or all outside it (-> F, one factor per element and tile, made at tile
+// start) in ONE op: x[e] *= G[unit(e)][tid] * F[e].  `um`: the units that hold a non-trivial factor.
+template <typename T, bool HASF>
+__device__ __forceinline__ void op_diagf(Cx<T> (&x)[Lay<T>::N], const Cx<T> *__restrict__ gp, int stride, uint32_t um,
+                                         bool has_g, const Cx<T> *fp) {
+#pragma unroll
+    for (int c = 0; c < 16; c += 8) {
+        if constexpr (sizeof(T) == 8) {
+            Cx<T> z[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                z[k].re = T(1); z[k].im = T(0);
+                if (has_g && ((um >> (c + k)) & 1u)) z[k] = ldg_cx(gp + (c + k) * stride);
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                if (!((um >> (c + k)) & 1u)) continue;
+                if (HASF) z[k] = cx_mul<T>(z[k], fp[c + k]);
+                cmul_inplace<T>(x[c + k], z[k].re, z[k].im);
+            }
+        } else {
+            float4 z[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                z[k] = make_float4(1.f, 0.f, 1.f, 0.f);
+                if (has_g && ((um >> (c + k)) & 1u)) z[k] = ldg_f4(gp + 2 * (c + k) * stride);
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                if (!((um >> (c + k)) & 1u)) continue;
+                Cx<T> z0, z1;
+                z0.re = z[k].x; z0.im = z[k].y; z1.re = z[k].z; z1.im = z[k].w;
+                if (HASF) { z0 = cx_mul<T>(z0, fp[2 * (c + k)]); z1 = cx_mul<T>(z1, fp[2 * (c + k) + 1]); }
+                cmul_inplace<T>(x[2 * (c + k)], z0.re, z0.im);
+                cmul_inplace<T>(x[2 * (c + k) + 1], z1.re, z1.im);
+            }
+        }
+    }
+}
+
 __device__ __forceinline__ int field_of(uint32_t base, uint32_t fl) {
     return int(((base >> (fl & 255u)) & ((1u << ((fl >> 8) & 255u)) - 1u)) << (fl >> 16));
 }
@@ -500,7 +612,8 @@ k_pass(Cx<T> *__restrict__ state, const __grid_constant__ PassGeom pg, const uin
     uint4 *const tilev = reinterpret_cast<uint4 *>(smem_raw);
     uint4 *const prog = tilev + nvec;
     uint4 *const s_H = prog + pg.blob_units;                                        // one 16-byte slot per factor
-    int64_t *const s_runoff = reinterpret_cast<int64_t *>(s_H + pg.nH);             // in vectors
+    Cx<T> *const s_F = reinterpret_cast<Cx<T> *>(s_H + pg.nH);                      // N factors per fused diagonal
+    int64_t *const s_runoff = reinterpret_cast<int64_t *>(s_F + pg.nF * N);         // in vectors
     int32_t *const s_outer = reinterpret_cast<int32_t *>(s_runoff + (1 << pg.nh));
     uint4 *const gvec = reinterpret_cast<uint4 *>(state);
 
@@ -518,6 +631,8 @@ k_pass(Cx<T> *__restrict__ state, const __grid_constant__ PassGeom pg, const uin
     const uint4 *const outers = prog + hdr.w;
     const int nH = int(prog[1].x);
     const uint4 *const hents = prog + prog[1].y;
+    const int nF = int(prog[1].z);
+    const uint4 *const fents = prog + prog[1].w;
 
     // (the launch uses exactly one thread per 16 vectors of the tile: every thread is live)
     const bool fast_io = nthr >= 8 && nthr >= (1 << rv) && nvec == 16 * nthr;   // 16 vectors per thread
@@ -567,6 +682,21 @@ k_pass(Cx<T> *__restrict__ state, const __grid_constant__ PassGeom pg, const uin
             }
             *reinterpret_cast<Cx<T> *>(s_H + m) = acc;
         }
+        // per-tile, per-element factors of the fused diagonals
+        for (int m = tid; m < nF * N; m += nthr) {
+            const int f = m / N, e = m % N;
+            const uint4 dir = fents[f];
+            Cx<T> acc;
+            acc.re = T(1); acc.im = T(0);
+            for (uint32_t sl = 0; sl < dir.y; sl++) {
+                const uint4 u = fents[dir.x + sl];
+                if (!((u.x >> e) & 1u)) continue;
+                const int32_t v = outer_value(outers, int(u.z), base_amp);
+                if (v < 0) continue;
+                acc = cx_mul<T>(acc, ldg_cx(tables + u.y + v));
+            }
+            s_F[m] = acc;
+        }
         cp_async_wait_all();
         __syncthreads();
 
@@ -613,7 +743,7 @@ k_pass(Cx<T> *__restrict__ state, const __grid_constant__ PassGeom pg, const uin
                     const uint32_t code = h0.x & 0xffffu;
                     uint32_t emask = h0.w;
                     int oi = 0;
-                    if (code != C_PHASE && (h0.z != 0u || (h0.y & 0xffffu) != 0xffffu)) {   // predicated op
+                    if (code != C_PHASE && code != C_DIAGF && (h0.z != 0u || (h0.y & 0xffffu) != 0xffffu)) {   // predicated op
                         const uint32_t oslot = h0.y & 0xffffu, tmask = h0.z;
                         bool ok = (base & tmask) == tmask;
                         if (oslot != 0xffffu) {
@@ -627,12 +757,15 @@ k_pass(Cx<T> *__restrict__ state, const __grid_constant__ PassGeom pg, const uin
 #define QJ_P1(A) op_perm1<T, A>(x, emask)
 #define QJ_D2(A, B) op_dense2<T, A, B>(x, pay, emask)
 #define QJ_P2(A, B) op_perm2<T, A, B>(x, emask)
+#define QJ_D2R(A, B) op_dense2r<T, A, B>(x, pay, emask)
                         case C_GROUP1C: op_group1<T, 0>(x, pay, h0.y >> 16, emask); break;
                         case C_GROUP1R: op_group1<T, 1>(x, pay, h0.y >> 16, emask); break;
                         case C_GROUP1X: op_group1<T, 2>(x, pay, h0.y >> 16, emask); break;
                         QJ_SLOT_CASES(C_PERM1, QJ_P1)
                         QJ_PAIR_CASES(C_DENSE2, QJ_D2)
                         QJ_PAIR_CASES(C_PERM2, QJ_P2)
+                        QJ_PAIR_CASES(C_DENSE2R, QJ_D2R)
+#undef QJ_D2R
 #undef QJ_P1
 #undef QJ_D2
 #undef QJ_P2
@@ -744,6 +877,12 @@ k_pass(Cx<T> *__restrict__ state, const __grid_constant__ PassGeom pg, const uin
                             emask = n0.w;
                             gcur = gnext;
                           }
+                        } break;
+                        case C_DIAGF: {   // h0.y = F index (0xffff: none) | has_g << 16, h0.w = unit mask, h1.x = G
+                            const uint32_t fidx = h0.y & 0xffffu;
+                            const Cx<T> *const gp = tables + h1.x + tid * (VS ? 2 : 1);
+                            if (fidx != 0xffffu) op_diagf<T, true>(x, gp, nthr, h0.w, (h0.y >> 16) != 0u, s_F + fidx * N);
+                            else op_diagf<T, false>(x, gp, nthr, h0.w, true, nullptr);
                         } break;
                         default: {  // C_DIAGN: table index = outer part | fields of the base | element part
                             const int nf = int(h0.y >> 16);
@@ -949,6 +1088,11 @@ static int program_build(qj_handle *h, int dtype, int nqubits, const qj_pass_des
     enc.hdata = static_cast<const unsigned char *>(data);
     enc.ndata = ndata;
 
+    // fused diagonals (C_DIAGF) replace the phase groups waiting at one point of a round when there
+    // are at least this many of them (0: never); QJ_DIAGF_MIN overrides it for experiments
+    int fuse_min = 2;
+    if (const char *ev = getenv("QJ_DIAGF_MIN")) fuse_min = atoi(ev);
+
     auto *prog = new qj_program();
     prog->dtype = dtype;
     prog->nqubits = nqubits;
@@ -991,6 +1135,7 @@ static int program_build(qj_handle *h, int dtype, int nqubits, const qj_pass_des
 
         // one launch = the rounds whose image fits the shared-memory budget
         std::vector<Unit> round_units, outer_units, op_units, h_units;
+        std::vector<Unit> f_dir, f_slices;   // fused diagonals with an outer part: directory + slices
         int launch_rounds = 0, launch_ops = 0;
         auto close_launch = [&]() {
             if (launch_rounds == 0) return;
@@ -999,16 +1144,21 @@ static int program_build(qj_handle *h, int dtype, int nqubits, const qj_pass_des
             memset(&hdr1, 0, sizeof(hdr1));
             const uint32_t off_rounds = 2, off_outer = off_rounds + uint32_t(round_units.size());
             const uint32_t off_h = off_outer + uint32_t(outer_units.size());
-            const uint32_t off_ops = off_h + uint32_t(h_units.size());
+            const uint32_t off_f = off_h + uint32_t(h_units.size());
+            const uint32_t off_ops = off_f + uint32_t(f_dir.size() + f_slices.size());
             hdr.w[0] = uint32_t(launch_rounds); hdr.w[1] = uint32_t(outer_units.size() / 2);
             hdr.w[2] = off_rounds; hdr.w[3] = off_outer;
             hdr1.w[0] = uint32_t(h_units.size() / 4); hdr1.w[1] = off_h;
+            hdr1.w[2] = uint32_t(f_dir.size()); hdr1.w[3] = off_f;
+            for (Unit &d : f_dir) d.w[0] += uint32_t(f_dir.size());   // slices follow the directory
             img.push_back(hdr);
             img.push_back(hdr1);
             for (size_t i = 0; i < round_units.size(); i += 3) round_units[i].w[0] += off_ops;   // first_unit
             img.insert(img.end(), round_units.begin(), round_units.end());
             img.insert(img.end(), outer_units.begin(), outer_units.end());
             img.insert(img.end(), h_units.begin(), h_units.end());
+            img.insert(img.end(), f_dir.begin(), f_dir.end());
+            img.insert(img.end(), f_slices.begin(), f_slices.end());
             img.insert(img.end(), op_units.begin(), op_units.end());
             qj_program::Launch L;
             L.geom = geo;
@@ -1017,11 +1167,13 @@ static int program_build(qj_handle *h, int dtype, int nqubits, const qj_pass_des
             L.nrounds = launch_rounds;
             L.nops = launch_ops;
             L.geom.nH = int(h_units.size() / 4);
-            L.smem = (size_t(1) << Tv) * 16 + img.size() * 16 + (h_units.size() / 4) * 16 + (size_t(8) << geo.nh) +
-                     (outer_units.size() / 2) * 4 + 16;
+            L.geom.nF = int(f_dir.size());
+            L.smem = (size_t(1) << Tv) * 16 + img.size() * 16 + (h_units.size() / 4) * 16 + f_dir.size() * 256 +
+                     (size_t(8) << geo.nh) + (outer_units.size() / 2) * 4 + 16;
             prog->launches.push_back(L);
             blob_all.insert(blob_all.end(), img.begin(), img.end());
             round_units.clear(); outer_units.clear(); op_units.clear(); h_units.clear();
+            f_dir.clear(); f_slices.clear();
             launch_rounds = 0; launch_ops = 0;
         };
 
@@ -1120,6 +1272,8 @@ static int program_build(qj_handle *h, int dtype, int nqubits, const qj_pass_des
             std::vector<PendingSlice> pending;
             std::vector<Unit> r_H;          // per-tile factor entries of this round (4 units each)
             const int h_base = int(h_units.size() / 4);
+            std::vector<Unit> r_Fdir, r_Fsl;   // fused diagonals of this round with an outer part
+            const int f_base = int(f_dir.size());
             const int nthr_round = 1 << int(tq.size());
             auto host_field = [](uint32_t base, uint32_t fl) -> uint32_t {
                 return ((base >> (fl & 255u)) & ((1u << ((fl >> 8) & 255u)) - 1u)) << (fl >> 16);
@@ -1143,6 +1297,78 @@ static int program_build(qj_handle *h, int dtype, int nqubits, const qj_pass_des
             };
             auto flush_pending = [&]() {
                 if (!pending.empty()) group_run.clear();
+                // ---- fused diagonal: when several groups (different element sets) wait here, the
+                // thread-only slices become ONE per-unit, per-thread factor array and the outer-only
+                // slices one per-element, per-tile factor array: one dispatch, one multiply per element
+                {
+                    std::vector<uint32_t> masks;
+                    bool any_f = false;
+                    for (const PendingSlice &ps : pending) {
+                        if (ps.cls == 2 || ps.sign) continue;
+                        if (std::find(masks.begin(), masks.end(), ps.emask) == masks.end()) masks.push_back(ps.emask);
+                        any_f = any_f || ps.cls == 1;
+                    }
+                    if (fuse_min > 0 && int(masks.size()) >= fuse_min) {
+                        std::vector<PendingSlice> keep;
+                        std::vector<const PendingSlice *> gm, fm;
+                        for (const PendingSlice &ps : pending) {
+                            if (ps.cls == 0) gm.push_back(&ps);
+                            else if (ps.cls == 1 && any_f) fm.push_back(&ps);
+                            else keep.push_back(ps);
+                        }
+                        uint32_t emu = 0;
+                        for (const PendingSlice *ps : gm) emu |= ps->emask;
+                        for (const PendingSlice *ps : fm) emu |= ps->emask;
+                        uint32_t um = 0;
+                        for (int u = 0; u < 16; u++)
+                            if ((emu >> (u << VS)) & (VS ? 3u : 1u)) um |= 1u << u;
+                        uint32_t g_off = 0xffffffffu;
+                        if (!gm.empty()) {
+                            const int upe = 1 << VS;   // elements per 16-byte unit
+                            std::vector<cd> G(size_t(16) * size_t(nthr_round) * size_t(upe), cd(1.0));
+                            for (const PendingSlice *ps : gm) {
+                                for (int t = 0; t < nthr_round; t++) {
+                                    uint32_t base = 0;
+                                    for (size_t kb = 0; kb < tq.size(); kb++) if ((t >> kb) & 1) base |= 1u << (tq[kb] + VS);
+                                    if ((base & ps->tmask) != ps->tmask) continue;
+                                    uint32_t idx = 0;
+                                    for (int f = 0; f < ps->nf; f++) idx |= host_field(base, ps->fields[f]);
+                                    const cd z = ps->host[idx];
+                                    for (int e = 0; e < N; e++)
+                                        if ((ps->emask >> e) & 1u)
+                                            G[(size_t(e >> VS) * size_t(nthr_round) + size_t(t)) * size_t(upe) + size_t(e & (upe - 1))] *= z;
+                                }
+                            }
+                            if (VS && ((enc.tables.size() / enc.esz) & 1)) enc.push_table(std::vector<cd>(1, cd(1.0)));   // 16-byte alignment
+                            g_off = enc.push_table(G);
+                        }
+                        uint32_t fidx = 0xffffu;
+                        if (!fm.empty()) {
+                            fidx = uint32_t(f_base) + uint32_t(r_Fdir.size());
+                            Unit d;
+                            memset(&d, 0, sizeof(d));
+                            d.w[0] = uint32_t(r_Fsl.size());      // round-relative; rebased when the round is appended
+                            d.w[1] = uint32_t(fm.size());
+                            r_Fdir.push_back(d);
+                            for (const PendingSlice *ps : fm) {
+                                Unit u;
+                                memset(&u, 0, sizeof(u));
+                                u.w[0] = ps->emask; u.w[1] = ps->table; u.w[2] = uint32_t(ps->oslot);
+                                r_Fsl.push_back(u);
+                            }
+                        }
+                        Unit h0, h1;
+                        memset(&h1, 0, sizeof(h1));
+                        h0.w[0] = uint32_t(C_DIAGF) | (2u << 16);
+                        h0.w[1] = fidx | ((gm.empty() ? 0u : 1u) << 16);
+                        h0.w[2] = 0;
+                        h0.w[3] = um;
+                        h1.w[0] = g_off;
+                        r_ops.push_back(h0); r_ops.push_back(h1);
+                        r_nops++;
+                        pending = keep;
+                    }
+                }
                 std::vector<bool> done(pending.size(), false);
                 for (size_t i = 0; i < pending.size(); i++) {
                     if (done[i]) continue;
@@ -1332,8 +1558,17 @@ static int program_build(qj_handle *h, int dtype, int nqubits, const qj_pass_des
                         if (is_swap) {
                             push_op(C_PERM2 + pair_index(a, b), oslot, 0, tmask, cmask_e, 0, nullptr, payload);
                         } else {
-                            enc.push_complex(payload, m);
-                            push_op(C_DENSE2 + pair_index(a, b), oslot, 0, tmask, cmask_e, 0, nullptr, payload);
+                            bool real4 = true;
+                            for (const cd &z : m) real4 = real4 && z.imag() == 0.0;
+                            if (real4) {
+                                std::vector<double> sc;
+                                for (const cd &z : m) sc.push_back(z.real());
+                                enc.push_scalars(payload, sc);
+                                push_op(C_DENSE2R + pair_index(a, b), oslot, 0, tmask, cmask_e, 0, nullptr, payload);
+                            } else {
+                                enc.push_complex(payload, m);
+                                push_op(C_DENSE2 + pair_index(a, b), oslot, 0, tmask, cmask_e, 0, nullptr, payload);
+                            }
                         }
                     }
                 } else if (od.kind == QJ_OPK_DIAG) {
@@ -1452,9 +1687,12 @@ static int program_build(qj_handle *h, int dtype, int nqubits, const qj_pass_des
             flush_pending();
 
             // append the round (closing the launch first when the image would overflow)
+            const size_t f_units = f_dir.size() + f_slices.size() + r_Fdir.size() + r_Fsl.size();
             const size_t need_units = 2 + round_units.size() + 3 + outer_units.size() + r_outer.size() + h_units.size() +
-                                      r_H.size() + op_units.size() + r_ops.size() + (h_units.size() + r_H.size()) / 4;
-            if (3 + r_outer.size() + r_ops.size() + r_H.size() + r_H.size() / 4 + 2 > size_t(kMaxBlobUnits) ||
+                                      r_H.size() + op_units.size() + r_ops.size() + (h_units.size() + r_H.size()) / 4 +
+                                      f_units + 16 * (f_dir.size() + r_Fdir.size());
+            if (3 + r_outer.size() + r_ops.size() + r_H.size() + r_H.size() / 4 + 2 + 17 * r_Fdir.size() + r_Fsl.size() >
+                    size_t(kMaxBlobUnits) ||
                 r_outer.size() / 2 > size_t(kMaxOuter))
                 return bail("round: too many ops for one round");
             if (need_units > size_t(kMaxBlobUnits) || (outer_units.size() + r_outer.size()) / 2 > size_t(kMaxOuter)) {
@@ -1472,12 +1710,16 @@ static int program_build(qj_handle *h, int dtype, int nqubits, const qj_pass_des
                             if (oslot != 0xffffu) r_ops[d].w[1] = nf | ((oslot - uint32_t(outer_base)) << 16);
                             d += (nf > 5) ? 3 : 2;
                         }
+                    } else if ((r_ops[i].w[0] & 0xffffu) == uint32_t(C_DIAGF)) {   // index of its per-tile factors
+                        const uint32_t fidx = r_ops[i].w[1] & 0xffffu;
+                        if (fidx != 0xffffu) r_ops[i].w[1] = (r_ops[i].w[1] & 0xffff0000u) | (fidx - uint32_t(f_base));
                     } else {
                         const uint32_t oslot = r_ops[i].w[1] & 0xffffu;
                         if (oslot != 0xffffu) r_ops[i].w[1] = (r_ops[i].w[1] & 0xffff0000u) | (oslot - uint32_t(outer_base));
                     }
                     i += units;
                 }
+                for (Unit &u : r_Fsl) u.w[2] -= uint32_t(outer_base);
                 for (size_t e = 0; e < r_H.size(); e += 4) {
                     const uint32_t ntab = r_H[e].w[0];
                     for (uint32_t t = 0; t < ntab; t++) r_H[e + 1 + t / 2].w[(t & 1) * 2 + 1] -= uint32_t(outer_base);
@@ -1497,6 +1739,9 @@ static int program_build(qj_handle *h, int dtype, int nqubits, const qj_pass_des
                 round_units.push_back(u0); round_units.push_back(u1); round_units.push_back(u2);
                 outer_units.insert(outer_units.end(), r_outer.begin(), r_outer.end());
                 h_units.insert(h_units.end(), r_H.begin(), r_H.end());
+                for (Unit &d : r_Fdir) d.w[0] += uint32_t(f_slices.size());
+                f_dir.insert(f_dir.end(), r_Fdir.begin(), r_Fdir.end());
+                f_slices.insert(f_slices.end(), r_Fsl.begin(), r_Fsl.end());
                 op_units.insert(op_units.end(), r_ops.begin(), r_ops.end());
                 launch_rounds++;
                 launch_ops += r_nops;

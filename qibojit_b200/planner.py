@@ -365,8 +365,183 @@ def fuse_one_qubit_runs(ops):
     return out
 
 
+# ------------------------------------------------------------------------------- pair blocks
+# Cost model of the pass kernel in issue cycles per thread and op (both dtypes: a thread holds 16
+# complex128 / 32 complex64 amplitudes and the FP64 / packed-FP32x2 pipes issue every other cycle):
+# what `fuse_pair_blocks` weighs a 4x4 block against.
+_COST_REAL1, _COST_CPLX1 = 128.0, 256.0      # one-target gate: real or axis-aligned / complex
+_COST_REAL2, _COST_CPLX2 = 256.0, 512.0      # two-target gate: real / complex 4x4
+_COST_DISPATCH = 60.0                        # header decode + branch of one op
+_COST_GROUPED = 20.0                         # share of a dispatch for a one-target gate (grouped by up to J)
+_COST_SIGN, _COST_PHASE = 80.0, 130.0        # +-1 diagonal / general phase op
+_PAIR_MARGIN = 1.25                          # fuse only when the separate ops cost this much more
+
+
+def _is_real(m):
+    return not np.any(np.asarray(m).imag)
+
+
+def _op_cost(op):
+    d = np.asarray(op.data)
+    if op.kind == "diag":
+        return _COST_SIGN if np.all((d.imag == 0) & (np.abs(d.real) == 1)) else _COST_PHASE
+    scale = 0.5 ** len(op.controls)
+    if len(op.targets) == 1:
+        m = d.reshape(2, 2)
+        if np.array_equal(m, [[0, 1], [1, 0]]):
+            return _COST_DISPATCH
+        axis = not (m[0, 0].imag or m[1, 1].imag or m[0, 1].real or m[1, 0].real)
+        body = _COST_REAL1 if (_is_real(m) or axis) else _COST_CPLX1
+        return body * scale + (_COST_DISPATCH if op.controls else _COST_GROUPED)
+    m = d.reshape(4, 4)
+    if np.array_equal(m, _SWAP_MATRIX):
+        return _COST_DISPATCH
+    return (_COST_REAL2 if _is_real(m) else _COST_CPLX2) * scale + _COST_DISPATCH
+
+
+def op_matrix(op, bits):
+    """Matrix of a dense / diagonal PlanOp on the index bits `bits` (matrix-index bit j <-> bits[j];
+    every bit of the op must be among them)."""
+    k = len(bits)
+    pos = {b: i for i, b in enumerate(bits)}
+    dim = 1 << k
+    out = np.zeros((dim, dim), dtype=np.complex128)
+    data = np.asarray(op.data, dtype=np.complex128)
+    nt = len(op.targets)
+    tmask = 0
+    for t in op.targets:
+        tmask |= 1 << pos[t]
+    for x in range(dim):
+        if any(not (x >> pos[c]) & 1 for c in op.controls):
+            out[x, x] = 1.0
+            continue
+        xin = 0
+        for j, t in enumerate(op.targets):
+            xin |= ((x >> pos[t]) & 1) << j
+        if op.kind == "diag":
+            out[x, x] = data.reshape(-1)[xin]
+            continue
+        m = data.reshape(1 << nt, 1 << nt)
+        for yout in range(1 << nt):
+            y = x & ~tmask
+            for j, t in enumerate(op.targets):
+                y |= ((yout >> j) & 1) << pos[t]
+            out[y, x] = m[yout, xin]
+    return out
+
+
+def fuse_pair_blocks(ops):
+    """Multiply runs of one- and two-bit ops on the same pair of index bits into ONE 4x4 dense op
+    where the pass kernel runs that faster than the separate ops (a real 4x4 costs 8 multiply-adds
+    per amplitude -- as much as two real rotations -- so RY RY CZ RY RY on a pair halves the
+    arithmetic; qibo's ``Circuit.fuse(max_qubits=2)`` forms the same blocks unconditionally).
+
+    A block grows from a two-bit op (the anchor) over the ops that are adjacent to it on both bits'
+    timelines, so every member can be moved to the anchor's position without crossing an op it
+    does not commute with.  Candidate blocks are taken best-gain first (lazy greedy: a candidate
+    whose members were claimed meanwhile is re-evaluated) and only when the separate ops cost
+    `_PAIR_MARGIN` times the block."""
+    import heapq
+
+    n = len(ops)
+    if any(op.kind == "raw" for op in ops):
+        # a raw gate's qubits are unknown here: fuse the stretches between raw gates
+        out, seg = [], []
+        for op in ops:
+            if op.kind == "raw":
+                out.extend(fuse_pair_blocks(seg))
+                out.append(op)
+                seg = []
+            else:
+                seg.append(op)
+        out.extend(fuse_pair_blocks(seg))
+        return out
+    timeline = {}
+    where = [dict() for _ in range(n)]     # op -> {bit: position in the bit's timeline}
+    for i, op in enumerate(ops):
+        for b in op.bits:
+            tl = timeline.setdefault(b, [])
+            where[i][b] = len(tl)
+            tl.append(i)
+
+    def single(op):
+        return len(op.bits) == 1 and not op.controls
+
+    free = [True] * n
+
+    def grow(anchor):
+        a, b = sorted(ops[anchor].bits)
+        pair = frozenset((a, b))
+        members = {anchor}
+        first = {a: where[anchor][a], b: where[anchor][b]}
+        last = dict(first)
+        for step, edge in ((-1, first), (1, last)):
+            moved = True
+            while moved:
+                moved = False
+                cand = {}
+                for bit in (a, b):
+                    p = edge[bit] + step
+                    if 0 <= p < len(timeline[bit]):
+                        cand[bit] = timeline[bit][p]
+                for bit, j in cand.items():
+                    if not free[j] or j in members:
+                        continue
+                    if single(ops[j]):
+                        members.add(j)
+                        edge[bit] += step
+                        moved = True
+                    elif ops[j].bits == pair and cand.get(a) == j and cand.get(b) == j:
+                        members.add(j)
+                        edge[a] += step
+                        edge[b] += step
+                        moved = True
+                        break
+        return sorted(members), (a, b)
+
+    def evaluate(anchor):
+        members, (a, b) = grow(anchor)
+        if len(members) < 2:
+            return None
+        m = np.eye(4, dtype=np.complex128)
+        for j in members:
+            m = op_matrix(ops[j], (a, b)) @ m
+        m[np.abs(m) < 1e-300] = 0.0
+        separate = sum(_op_cost(ops[j]) for j in members)
+        if not np.any(m - np.diag(np.diagonal(m))):
+            fused = PlanOp("diag", (a, b), (), np.diagonal(m).copy())
+        else:
+            fused = PlanOp("dense", (a, b), (), m)
+        cost = _op_cost(fused)
+        if separate < _PAIR_MARGIN * cost:
+            return None
+        return separate - cost, members, fused
+
+    heap = []
+    for i, op in enumerate(ops):
+        if len(op.bits) == 2 and op.kind in ("dense", "diag"):
+            ev = evaluate(i)
+            if ev is not None:
+                heapq.heappush(heap, (-ev[0], i, tuple(ev[1])))
+    replaced = {}
+    while heap:
+        _, i, members = heapq.heappop(heap)
+        if not free[i]:
+            continue
+        ev = evaluate(i)
+        if ev is None:
+            continue
+        if tuple(ev[1]) != members:           # shrunk since it was queued: back into the queue
+            heapq.heappush(heap, (-ev[0], i, tuple(ev[1])))
+            continue
+        for j in ev[1]:
+            free[j] = False
+        replaced[i] = ev[2]
+    return [replaced.get(i, op) for i, op in enumerate(ops) if free[i] or i in replaced]
+
+
 def plan_queue(queue, nqubits, matrices, tile_bits, run_bits, max_diag_bits=10, dtype="complex128",
-               zero_state=False):
+               zero_state=False, pair_blocks=True):
     """Gate queue -> [('pass', local_bits, [(reg_bits, [PlanOp])]) | ('raw', gate)] (host logic).
     `zero_state`: the program will only ever run on |0...0> (SWAP gates become relabellings)."""
     ops = []
@@ -375,6 +550,8 @@ def plan_queue(queue, nqubits, matrices, tile_bits, run_bits, max_diag_bits=10, 
     if zero_state:
         ops = relabel_swaps_away(ops, nqubits)
     ops = fuse_one_qubit_runs(ops)
+    if pair_blocks:
+        ops = fuse_pair_blocks(ops)
     nreg = REG_BITS[str(dtype)]
     fixed = (0,) if str(dtype) == "complex64" else ()
     mdb = min(max_diag_bits, _capi.QJ_MAX_DIAG_BITS)
@@ -399,8 +576,9 @@ class Program:
     per-gate kernels execute (dense gates on >= 3 targets, measurements)."""
 
     def __init__(self, backend, queue, nqubits, dtype=None, tile_bits=None, run_bits=None,
-                 max_diag_bits=10, zero_state=False):
+                 max_diag_bits=10, zero_state=False, pair_blocks=True):
         self.backend = backend
+        self.pair_blocks = bool(pair_blocks)
         self.zero_state = bool(zero_state)   # valid on |0...0> only (SWAP gates relabelled away)
         self.nqubits = int(nqubits)
         self.dtype = str(dtype or backend.dtype)
@@ -416,7 +594,8 @@ class Program:
             return
         pending = []
         for seg in plan_queue(queue, self.nqubits, backend.custom_matrices, self.tile_bits,
-                              self.run_bits, self.max_diag_bits, self.dtype, self.zero_state):
+                              self.run_bits, self.max_diag_bits, self.dtype, self.zero_state,
+                              self.pair_blocks):
             if seg[0] == "raw":
                 self._flush(pending)
                 pending = []
@@ -517,7 +696,7 @@ class Program:
     def fma_per_amplitude(self):
         """Real multiply-adds per amplitude the pass kernel executes for this program (the
         arithmetic side of the roofline): 4 for a real or axis-aligned one-target gate, 8 for a
-        complex one, 16 for a two-target gate, 4 per phase multiply; permutations and sign flips
+        complex one, 16 for a two-target gate (8 when its matrix is real), 4 per phase multiply; permutations and sign flips
         cost none; controls scale by 2^-c."""
         total = 0.0
         for _, rounds in self.passes:
@@ -536,7 +715,7 @@ class Program:
                         m = d.reshape(4, 4)
                         if np.array_equal(m, [[1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]]):
                             continue            # SWAP: register renaming
-                        total += 16.0 * frac
+                        total += (8.0 if not np.any(m.imag) else 16.0) * frac
                     elif op.kind == "diag":
                         if np.all((d.imag == 0) & (np.abs(d.real) == 1)):
                             continue

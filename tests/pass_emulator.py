@@ -16,6 +16,7 @@ import numpy as np
 from qibojit_b200 import _capi, planner
 
 C_GROUP1C, C_GROUP1R, C_GROUP1X, C_PERM1, C_DENSE2, C_PERM2, C_PHASE, C_DIAGN = 0, 1, 2, 3, 8, 18, 28, 29
+C_DENSE2R, C_DIAGF = 30, 40
 SEL_ALL, SEL_SLOT, SEL_PAIR, SEL_MASK = 0, 1, 6, 16
 PAIRS = [(0, 1), (0, 2), (1, 2), (0, 3), (1, 3), (2, 3), (0, 4), (1, 4), (2, 4), (3, 4)]
 
@@ -109,6 +110,7 @@ def run_image(image, state):
         nthr = max(1, (1 << Tv) >> 4)
         nrounds, nouter, off_rounds, off_outer = (int(x) for x in U[0])
         nH, off_H = int(U[1][0]), int(U[1][1])
+        nF, off_F = int(U[1][2]), int(U[1][3])
         gbit = list(range(r)) + L["hibit"][:nh]            # local amplitude position -> index bit
         assert L["smem"] <= 200 << 10
 
@@ -147,6 +149,16 @@ def run_image(image, state):
                     if v >= 0:
                         acc *= image.tables[table + v]
                 s_H.append(acc)
+            s_F = np.ones((nF, N), dtype=np.complex128)     # per-tile, per-element factors of the fused diagonals
+            for f in range(nF):
+                first, nsl = int(U[off_F + f][0]), int(U[off_F + f][1])
+                for sl in U[off_F + first:off_F + first + nsl]:
+                    v = outer_value(int(sl[2]), base_amp)
+                    if v < 0:
+                        continue
+                    for ee in range(N):
+                        if (int(sl[0]) >> ee) & 1:
+                            s_F[f, ee] *= image.tables[int(sl[1]) + v]
 
             tid = np.arange(nthr)
             for rd in range(nrounds):
@@ -184,7 +196,7 @@ def run_image(image, state):
                     op += units
                     emask = np.full(nthr, int(h0[3]), dtype=np.int64)
                     oi = 0
-                    if code != C_PHASE and (int(h0[2]) != 0 or (int(h0[1]) & 0xffff) != 0xffff):
+                    if code not in (C_PHASE, C_DIAGF) and (int(h0[2]) != 0 or (int(h0[1]) & 0xffff) != 0xffff):
                         oslot, tmask = int(h0[1]) & 0xffff, int(h0[2])
                         ok = (base & tmask) == tmask
                         if oslot != 0xffff:
@@ -231,11 +243,16 @@ def run_image(image, state):
                             e1 = e0 | (1 << A)
                             m = sel_e[:, e0]
                             x[m, e0], x[m, e1] = x[m, e1].copy(), x[m, e0].copy()
-                    elif C_DENSE2 <= code < C_DENSE2 + 10 or C_PERM2 <= code < C_PERM2 + 10:
-                        perm = code >= C_PERM2
-                        a, b = PAIRS[code - (C_PERM2 if perm else C_DENSE2)]
+                    elif (C_DENSE2 <= code < C_DENSE2 + 10 or C_PERM2 <= code < C_PERM2 + 10
+                          or C_DENSE2R <= code < C_DENSE2R + 10):
+                        perm, real = C_PERM2 <= code < C_PERM2 + 10, code >= C_DENSE2R
+                        a, b = PAIRS[code - (C_DENSE2R if real else C_PERM2 if perm else C_DENSE2)]
                         if perm:
                             g = np.array([[1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]], dtype=np.complex128)
+                        elif real:      # 16 real scalars, row-major
+                            nu = 8 if image.c128 else 4
+                            assert units == 2 + nu
+                            g = image.scalars(U[pay:pay + nu])[:16].reshape(4, 4).astype(np.complex128)
                         else:
                             g = image.complex_elements(U[pay:pay + 16], 16).reshape(4, 4)
                         for e0 in range(N):
@@ -285,6 +302,21 @@ def run_image(image, state):
                             chosen = ((int(h0[3]) >> e) & 1).astype(bool)
                         assert np.array_equal(chosen, ((int(h0[3]) >> e) & 1).astype(bool))
                         x[:, chosen] *= ph[:, None]
+                    elif code == C_DIAGF:
+                        fidx, has_g, um = int(h0[1]) & 0xffff, int(h0[1]) >> 16, int(h0[3])
+                        upe = 1 << VS                               # elements per 16-byte unit
+                        for u in range(16):
+                            if not (um >> u) & 1:
+                                continue
+                            for k in range(upe):
+                                ee = u * upe + k
+                                z = np.ones(nthr, dtype=np.complex128)
+                                if has_g:
+                                    z = image.tables[int(h1[0]) + (u * nthr + tid) * upe + k]
+                                if fidx != 0xffff:
+                                    z = z * s_F[fidx, ee]
+                                x[:, ee] *= z
+                        assert units == 2
                     elif code == C_DIAGN:
                         nf = int(h0[1]) >> 16
                         f4, w = U[pay], U[pay + 1]

@@ -116,14 +116,18 @@ def test_fma_count_of_the_benchmark_circuits():
     """The arithmetic side of the roofline bench.py reports: 4 real FMAs per amplitude for a real
     or axis-aligned one-qubit gate, 8 for a complex one, 16 for a 4x4, none for sign flips."""
     class Stub(planner.Program):
-        def __init__(self, queue, n, dt):
+        def __init__(self, queue, n, dt, pair_blocks=True):
             self.passes = [(s[1], s[2]) for s in planner.plan_queue(
-                queue, n, CustomMatrices(dt), planner.DEFAULT_TILE_BITS[dt], planner.DEFAULT_RUN_BITS[dt], 10, dt)
+                queue, n, CustomMatrices(dt), planner.DEFAULT_TILE_BITS[dt], planner.DEFAULT_RUN_BITS[dt], 10, dt,
+                pair_blocks=pair_blocks)
                 if s[0] == "pass"]
             self.segments = []
 
     n = 20
-    assert Stub(circuits.variational(n).queue, n, "complex128").fma_per_amplitude() == 5 * n * 4    # RY real, CZ = signs
+    var = circuits.variational(n).queue
+    assert Stub(var, n, "complex128", pair_blocks=False).fma_per_amplitude() == 5 * n * 4    # RY real, CZ = signs
+    # RY RY CZ RY RY on a pair = one real 4x4 (8 per amplitude instead of 16): two block layers + the last RY layer
+    assert Stub(var, n, "complex128").fma_per_amplitude() == 2 * (n // 2) * 8 + n * 4
     qv = circuits.quantum_volume(n, depth=3)
     assert Stub(qv.queue, n, "complex64").fma_per_amplitude() == len(qv.queue) * 16
     assert Stub([gates.X(0), gates.CNOT(1, 2), gates.SWAP(3, 4), gates.Z(5)], n, "complex128").fma_per_amplitude() == 0
@@ -198,7 +202,7 @@ def test_adjacent_one_qubit_gates_are_fused():
     n = 8
     glist = [gates.H(0), gates.RX(0, 0.3), gates.RZ(0, 0.2), gates.CZ(0, 1), gates.H(0), gates.H(1), gates.T(1),
              gates.RY(1, 0.4), gates.Z(2), gates.S(2)]
-    plan = planner.plan_queue(glist, n, MATS, 6, 3)
+    plan = planner.plan_queue(glist, n, MATS, 6, 3, pair_blocks=False)
     ops = _ops(plan)
     dense = [op for op in ops if op.kind == "dense"]
     assert len(dense) == 3                     # H.RX.RZ on qubit 0 | H on 0 after the CZ | H.T.RY on 1

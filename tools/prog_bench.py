@@ -32,6 +32,7 @@ def main():
     ap.add_argument("--diag-bits", type=int, default=10)
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--keep-swaps", action="store_true", help="do not compile for the |0...0> input (SWAP gates stay)")
+    ap.add_argument("--no-pair-blocks", action="store_true", help="keep one- and two-qubit gates apart (no 4x4 blocks)")
     ap.add_argument("--out", default="")
     args = ap.parse_args()
 
@@ -44,7 +45,7 @@ def main():
     t0 = time.perf_counter()
     prog = planner.Program(b, c.queue, n, dtype=args.dtype, tile_bits=args.tile_bits or None,
                            run_bits=args.run_bits or None, max_diag_bits=args.diag_bits,
-                           zero_state=not args.keep_swaps)
+                           zero_state=not args.keep_swaps, pair_blocks=not args.no_pair_blocks)
     t_plan = time.perf_counter() - t0
     stats = prog.stats()
     state = b.zero_state(n)
