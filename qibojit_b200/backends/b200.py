@@ -103,9 +103,14 @@ class B200Backend(_QiboBackend):
             self._handles[self._device_index] = h
         return h
 
+    def _handle_or_none(self):
+        """The current device's handle if it exists (never creates one: used on tear-down paths)."""
+        return getattr(self, "_handles", {}).get(getattr(self, "_device_index", None))
+
     def __del__(self):
         try:
-            for h in self._handles.values():
+            handles, self._handles = self._handles, {}     # nobody can pick up a destroyed handle
+            for h in handles.values():
                 self._lib.qj_destroy(h)
         except Exception:
             pass
@@ -688,20 +693,24 @@ class B200Backend(_QiboBackend):
 
     @staticmethod
     def circuit_fingerprint(queue):
-        """Hashable summary of a gate queue -- classes, qubits AND parameter values -- so that a
+        """Comparable summary of a gate queue -- classes, qubits AND parameter values -- so that a
         cached program is not reused after `circuit.set_parameters(...)` (the matrices are baked
-        into the program image)."""
+        into the program image).  The summary is the tuple itself, compared by value: Python's
+        hash() is no identity (hash(-1.0) == hash(-2.0)), so nothing here goes through it; arrays
+        enter as a blake2b digest of their bytes."""
+        import hashlib
+
         def param(p):
             if hasattr(p, "tobytes"):
                 a = np.ascontiguousarray(p)
-                return (a.shape, str(a.dtype), hash(a.tobytes()))
+                return (a.shape, str(a.dtype), hashlib.blake2b(a.tobytes(), digest_size=16).digest())
             if isinstance(p, (list, tuple)):
                 return tuple(param(x) for x in p)
-            try:
-                hash(p)
-                return p
-            except TypeError:
-                return repr(p)
+            if isinstance(p, (bool, int, float, complex, str, bytes, type(None))):
+                return (type(p).__name__, p)
+            if isinstance(p, np.generic):
+                return (p.dtype.str, p.tobytes())
+            return repr(p)
 
         out = []
         for g in queue:
@@ -710,7 +719,7 @@ class B200Backend(_QiboBackend):
             if hasattr(g, "gates"):               # FusedGate
                 item += (B200Backend.circuit_fingerprint(g.gates),)
             out.append(item)
-        return hash(tuple(out))
+        return tuple(out)
 
     def compile_circuit(self, circuit, **options):
         """Compile (and cache on the circuit object) the multi-gate pass program of `circuit`."""

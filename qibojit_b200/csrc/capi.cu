@@ -137,9 +137,16 @@ int qj_create(int device, void *stream, qj_handle **out) {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail(QJ_ERR_NODEVICE, "no CUDA device available (this library has no CPU fallback)");
-    QJ_REQUIRE(device >= 0 && device < ndev, "device ordinal out of range");
-    QJ_CUDA_OK(cudaSetDevice(device));
+    QJ_REQUIRE(device >= 0 && device < ndev && device < kMaxDevices, "device ordinal out of range");
     qj_handle *h = new qj_handle();
+    // allocate on `device`, give the caller's current device back on return
+    int prev_device = -1;
+    cudaGetDevice(&prev_device);
+    struct Restore {
+        int prev;
+        ~Restore() { if (prev >= 0) cudaSetDevice(prev); }
+    } restore{prev_device};
+    QJ_CUDA_OK(cudaSetDevice(device));
     h->device = device;
     cudaDeviceProp prop;
     QJ_CUDA_OK(cudaGetDeviceProperties(&prop, device));
@@ -159,6 +166,7 @@ int qj_create(int device, void *stream, qj_handle **out) {
 }
 
 int qj_destroy(qj_handle *h) {
+    qj::DeviceGuard device_guard(h);
     if (!h) return QJ_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
@@ -173,6 +181,7 @@ int qj_destroy(qj_handle *h) {
 }
 
 int qj_set_stream(qj_handle *h, void *stream) {
+    qj::DeviceGuard device_guard(h);
     QJ_REQUIRE(h != nullptr, "null handle");
     if (h->own_stream) {
         cudaStreamSynchronize(h->stream);
@@ -184,6 +193,7 @@ int qj_set_stream(qj_handle *h, void *stream) {
 }
 
 int qj_sync(qj_handle *h) {
+    qj::DeviceGuard device_guard(h);
     QJ_REQUIRE(h != nullptr, "null handle");
     QJ_CUDA_OK(cudaStreamSynchronize(h->stream));
     return QJ_OK;
@@ -192,6 +202,7 @@ int qj_sync(qj_handle *h) {
 int64_t qj_launch_count(qj_handle *h) { return h ? h->launches : 0; }
 
 int qj_set_route(qj_handle *h, int route) {
+    qj::DeviceGuard device_guard(h);
     QJ_REQUIRE(h != nullptr, "null handle");
     QJ_REQUIRE(route >= 0 && route <= 2, "route must be 0, 1 or 2");
     h->route = route;
@@ -200,23 +211,29 @@ int qj_set_route(qj_handle *h, int route) {
 
 int qj_apply_gate(qj_handle *h, void *state, int dtype, int nqubits, int m, const void *gate,
                   const int32_t *qubits, int nactive) {
+    qj::DeviceGuard device_guard(h);
     return one_target(h, state, dtype, nqubits, m, gate, qubits, nactive, 0);
 }
 int qj_apply_x(qj_handle *h, void *state, int dtype, int nqubits, int m, const int32_t *qubits, int nactive) {
+    qj::DeviceGuard device_guard(h);
     return one_target(h, state, dtype, nqubits, m, nullptr, qubits, nactive, OP_X);
 }
 int qj_apply_y(qj_handle *h, void *state, int dtype, int nqubits, int m, const int32_t *qubits, int nactive) {
+    qj::DeviceGuard device_guard(h);
     return one_target(h, state, dtype, nqubits, m, nullptr, qubits, nactive, OP_Y);
 }
 int qj_apply_z(qj_handle *h, void *state, int dtype, int nqubits, int m, const int32_t *qubits, int nactive) {
+    qj::DeviceGuard device_guard(h);
     return one_target(h, state, dtype, nqubits, m, nullptr, qubits, nactive, OP_Z);
 }
 int qj_apply_z_pow(qj_handle *h, void *state, int dtype, int nqubits, int m, const void *phase,
                    const int32_t *qubits, int nactive) {
+    qj::DeviceGuard device_guard(h);
     return one_target(h, state, dtype, nqubits, m, phase, qubits, nactive, OP_ZPOW);
 }
 
 int qj_apply_phase(qj_handle *h, void *state, int dtype, int nqubits, const void *phase) {
+    qj::DeviceGuard device_guard(h);
     int rc = check_common(h, state, dtype, nqubits);
     if (rc) return rc;
     QJ_REQUIRE(phase != nullptr, "null phase");
@@ -228,19 +245,23 @@ int qj_apply_phase(qj_handle *h, void *state, int dtype, int nqubits, const void
 
 int qj_apply_two_qubit_gate(qj_handle *h, void *state, int dtype, int nqubits, int m1, int m2,
                             int swap_targets, const void *gate, const int32_t *qubits, int nactive) {
+    qj::DeviceGuard device_guard(h);
     return two_target(h, state, dtype, nqubits, m1, m2, swap_targets, gate, qubits, nactive, 0);
 }
 int qj_apply_swap(qj_handle *h, void *state, int dtype, int nqubits, int m1, int m2,
                   const int32_t *qubits, int nactive) {
+    qj::DeviceGuard device_guard(h);
     return two_target(h, state, dtype, nqubits, m1, m2, 0, nullptr, qubits, nactive, OP_SWAP);
 }
 int qj_apply_fsim(qj_handle *h, void *state, int dtype, int nqubits, int m1, int m2, int swap_targets,
                   const void *gate, const int32_t *qubits, int nactive) {
+    qj::DeviceGuard device_guard(h);
     return two_target(h, state, dtype, nqubits, m1, m2, swap_targets, gate, qubits, nactive, OP_FSIM);
 }
 
 int qj_apply_multi_qubit_gate(qj_handle *h, void *state, int dtype, int nqubits, const void *gate,
                               const int32_t *qubits, int nactive, const int64_t *targets, int ntargets) {
+    qj::DeviceGuard device_guard(h);
     int rc = check_common(h, state, dtype, nqubits);
     if (rc) return rc;
     QJ_REQUIRE(gate != nullptr && targets != nullptr, "null gate or targets");

@@ -51,6 +51,26 @@ struct qj_handle {
 
 namespace qj {
 
+// Every entry point runs on its handle's device whatever device the calling thread had current
+// (the reference drives all devices from joblib threads of one process, gpu.py:688-694) and
+// leaves the caller's current device as it found it.
+constexpr int kMaxDevices = 64;
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(const qj_handle *h) {
+        if (h && cudaGetDevice(&prev) == cudaSuccess && prev != h->device) {
+            cudaSetDevice(h->device);
+            switched = true;
+        }
+    }
+    ~DeviceGuard() {
+        if (switched) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard &) = delete;
+    DeviceGuard &operator=(const DeviceGuard &) = delete;
+};
+
 constexpr int kMaxPos = QJ_MAX_QUBITS;
 constexpr int kMaxDirectTargets = 5;  // register ("direct") kernels: 2^5 amplitudes per thread
 

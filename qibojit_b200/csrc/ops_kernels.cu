@@ -474,6 +474,7 @@ int launch_checked(qj_handle *h, F &&f) {
 using namespace qj;
 
 extern "C" int qj_initial_state(qj_handle *h, void *state, int dtype, int nqubits) {
+    qj::DeviceGuard device_guard(h);
     QJ_REQUIRE(h && state, "null handle or state");
     QJ_REQUIRE(nqubits >= 0 && nqubits <= QJ_MAX_QUBITS, "nqubits out of range");
     const int64_t bytes = (int64_t(1) << nqubits) * (dtype == QJ_C128 ? 16 : 8);
@@ -531,6 +532,7 @@ int collapse_t(qj_handle *h, void *state, int nqubits, const int32_t *qubits, in
 
 extern "C" int qj_collapse_state(qj_handle *h, void *state, int dtype, int nqubits,
                                  const int32_t *qubits, int ntargets, int64_t result, int normalize) {
+    qj::DeviceGuard device_guard(h);
     QJ_REQUIRE(h && state && (qubits || ntargets == 0), "null argument");
     QJ_REQUIRE(ntargets >= 0 && ntargets <= nqubits && nqubits <= QJ_MAX_QUBITS, "bad qubit counts");
     if (dtype == QJ_C128) return collapse_t<double>(h, state, nqubits, qubits, ntargets, result, normalize);
@@ -539,6 +541,7 @@ extern "C" int qj_collapse_state(qj_handle *h, void *state, int dtype, int nqubi
 }
 
 extern "C" int qj_norm2(qj_handle *h, const void *state, int dtype, int nqubits, double *out) {
+    qj::DeviceGuard device_guard(h);
     QJ_REQUIRE(h && state && out, "null argument");
     const int64_t n = int64_t(1) << nqubits;
     const unsigned grid = persistent_grid(h, n, kThreads * 4);
@@ -607,6 +610,7 @@ int probs_t(qj_handle *h, const void *state, int nqubits, const int32_t *bits, i
 
 extern "C" int qj_calculate_probabilities(qj_handle *h, const void *state, int dtype, int nqubits,
                                           const int32_t *bits, int nmeas, void *probs) {
+    qj::DeviceGuard device_guard(h);
     QJ_REQUIRE(h && state && probs && (bits || nmeas == 0), "null argument");
     QJ_REQUIRE(nmeas >= 0 && nmeas <= nqubits && nqubits <= QJ_MAX_QUBITS, "bad qubit counts");
     if (dtype == QJ_C128) return probs_t<double>(h, state, nqubits, bits, nmeas, probs);
@@ -656,6 +660,7 @@ struct HostMT {
 extern "C" int qj_measure_frequencies(qj_handle *h, int64_t *frequencies, const void *probs,
                                       int real_dtype, int64_t nshots, int nqubits, int64_t seed,
                                       int nthreads) {
+    qj::DeviceGuard device_guard(h);
     QJ_REQUIRE(h && frequencies && probs, "null argument");
     QJ_REQUIRE(nthreads >= 1 && nthreads <= 4096, "nthreads out of range");
     QJ_REQUIRE(nshots >= 0 && nqubits >= 0 && nqubits <= QJ_MAX_QUBITS, "bad sampler arguments");
@@ -699,6 +704,7 @@ extern "C" int qj_measure_frequencies(qj_handle *h, int64_t *frequencies, const 
 extern "C" int qj_sample_shots(qj_handle *h, const void *probs, int real_dtype, int nqubits,
                                const double *uniforms, int64_t nshots, int64_t *shots,
                                double *cdf_scratch) {
+    qj::DeviceGuard device_guard(h);
     QJ_REQUIRE(h && probs && uniforms && shots && cdf_scratch, "null argument");
     const int64_t n = int64_t(1) << nqubits;
     const int64_t ntiles = (n + kScanTile - 1) / kScanTile;
@@ -740,6 +746,7 @@ int swap_geom(int dtype, int nlocal, int m, int *mv, int64_t *ngroups) {
 
 extern "C" int qj_swap_pieces_peer(qj_handle *h, void *local, void *peer, int dtype, int nlocal, int m,
                                    int is_upper) {
+    qj::DeviceGuard device_guard(h);
     QJ_REQUIRE(h && local && peer, "null argument");
     int mv; int64_t ngroups;
     int rc = swap_geom(dtype, nlocal, m, &mv, &ngroups);
@@ -784,10 +791,12 @@ int swap_pack_impl(qj_handle *h, const void *local, void *buf, int dtype, int nl
 
 extern "C" int qj_swap_pack(qj_handle *h, const void *local, void *buf, int dtype, int nlocal, int m,
                             int is_upper, int64_t chunk_begin, int64_t chunk_len) {
+    qj::DeviceGuard device_guard(h);
     return swap_pack_impl(h, local, buf, dtype, nlocal, m, is_upper, chunk_begin, chunk_len, 0);
 }
 extern "C" int qj_swap_unpack(qj_handle *h, void *local, const void *buf, int dtype, int nlocal, int m,
                               int is_upper, int64_t chunk_begin, int64_t chunk_len) {
+    qj::DeviceGuard device_guard(h);
     return swap_pack_impl(h, local, const_cast<void *>(buf), dtype, nlocal, m, is_upper, chunk_begin, chunk_len, 1);
 }
 
@@ -820,10 +829,12 @@ int swap_pack_bits_impl(qj_handle *h, const void *local, void *buf, int dtype, i
 
 extern "C" int qj_swap_pack_bits(qj_handle *h, const void *local, void *buf, int dtype, int nlocal,
                                  const int32_t *bits, int nbits, int value, int64_t chunk_begin, int64_t chunk_len) {
+    qj::DeviceGuard device_guard(h);
     return swap_pack_bits_impl(h, local, buf, dtype, nlocal, bits, nbits, value, chunk_begin, chunk_len, 0);
 }
 extern "C" int qj_swap_unpack_bits(qj_handle *h, void *local, const void *buf, int dtype, int nlocal,
                                    const int32_t *bits, int nbits, int value, int64_t chunk_begin, int64_t chunk_len) {
+    qj::DeviceGuard device_guard(h);
     return swap_pack_bits_impl(h, local, const_cast<void *>(buf), dtype, nlocal, bits, nbits, value, chunk_begin,
                                chunk_len, 1);
 }

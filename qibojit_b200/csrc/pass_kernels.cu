@@ -53,7 +53,14 @@ constexpr int kVecRegBits = 4;          // a thread holds 2^4 vectors per round
 constexpr int kMaxTileVecBits = 12;     // 64 KiB tiles
 constexpr int kMinTileBits = 6;
 constexpr int kMaxHiBits = 8;
-constexpr int kMaxBlobUnits = (40 << 10) / 16;   // program image in shared memory
+// The program image of a launch travels as a KERNEL PARAMETER (constant bank): op headers and
+// gate matrices are read with warp-uniform constant loads (LDCU) into uniform registers and feed
+// the FP instructions as uniform operands -- no shared-memory traffic, no vector registers and no
+// unpacking for them.  (Kernel parameters may total 32764 bytes.)
+constexpr int kMaxBlobUnits = 1984;              // 31 KiB
+struct ProgParam {
+    uint4 u[kMaxBlobUnits];
+};
 constexpr int kMaxOuter = 512;
 
 template <typename T>
@@ -80,7 +87,8 @@ enum {
     C_PHASE = 28,     // product of per-thread table look-ups, one complex multiply of the selected elements
     C_DIAGN = 29,     // general: one look-up per element
     C_DENSE2R = 30,   // + pair index: REAL 4x4 (16 scalars): half the multiply-adds of the complex one
-    C_DIAGF = 40,     // fused diagonal: per-thread, per-element factors G[unit][tid] (x per-tile factors)
+    C_DIAGF = 40,     // fused diagonal: per-thread, per-element factors G[tid][unit] (x per-tile factors)
+    C_DIAGC = 41,     // constant diagonal: one complex constant per selected unit, in the payload
 };
 
 // element selection of a C_PHASE op (which of a thread's register amplitudes the phase multiplies)
@@ -98,6 +106,7 @@ struct PassGeom {
     int pos[QJ_MAX_QUBITS];
     int64_t ntiles;
     int blob_units;        // program image, 16-byte units
+    int prefix_units;      // its leading part (header, rounds, outers, H and F entries): copied to shared memory
     int nH;                // per-tile phase factors (outer-only parts of the phase groups)
     int nF;                // fused diagonals with an outer part (2^J per-tile, per-element factors each)
 };
@@ -133,21 +142,21 @@ __device__ __forceinline__ void cmul_acc(T &ar, T &ai, T gr, T gi, T xr, T xi) {
 
 __device__ __forceinline__ constexpr int insert0(int p, int a) { return ((p >> a) << (a + 1)) | (p & ((1 << a) - 1)); }
 
-// payload readers: NW 32-bit words from 16-byte aligned shared memory (warp-uniform address)
+// payload readers: NU 16-byte units of the program image (constant bank, warp-uniform index)
 template <int NU>
-__device__ __forceinline__ void load_units(const uint4 *p, double (&d)[2 * NU]) {
+__device__ __forceinline__ void load_units(const ProgParam &pp, int p, double (&d)[2 * NU]) {
 #pragma unroll
     for (int i = 0; i < NU; i++) {
-        const uint4 q = p[i];
+        const uint4 q = pp.u[p + i];
         d[2 * i] = __hiloint2double(int(q.y), int(q.x));
         d[2 * i + 1] = __hiloint2double(int(q.w), int(q.z));
     }
 }
 template <int NU>
-__device__ __forceinline__ void load_units(const uint4 *p, float (&d)[4 * NU]) {
+__device__ __forceinline__ void load_units(const ProgParam &pp, int p, float (&d)[4 * NU]) {
 #pragma unroll
     for (int i = 0; i < NU; i++) {
-        const uint4 q = p[i];
+        const uint4 q = pp.u[p + i];
         d[4 * i] = __uint_as_float(q.x); d[4 * i + 1] = __uint_as_float(q.y);
         d[4 * i + 2] = __uint_as_float(q.z); d[4 * i + 3] = __uint_as_float(q.w);
     }
@@ -236,13 +245,13 @@ __device__ __forceinline__ void dense1_pair(Cx<T> &s0, Cx<T> &s1, const T *m) {
 }
 
 template <typename T, int A, int KIND>
-__device__ __forceinline__ void op_dense1(Cx<T> (&x)[Lay<T>::N], const uint4 *pay, uint32_t emask) {
+__device__ __forceinline__ void op_dense1(Cx<T> (&x)[Lay<T>::N], const ProgParam &pp, int pay, uint32_t emask) {
     constexpr int N = Lay<T>::N;
     if constexpr (A < Lay<T>::J) {
         // scalars in the payload (a whole number of units); complex64 complex elements are 4 floats
         constexpr int NS = (sizeof(T) == 4) ? (KIND == 0 ? 16 : KIND == 2 ? 8 : 4) : (KIND == 0 ? 8 : 4);
         T m[NS];
-        load_units<NS * sizeof(T) / 16>(pay, m);
+        load_units<NS * sizeof(T) / 16>(pp, pay, m);
         if (emask == (N == 32 ? 0xffffffffu : 0xffffu)) {
 #pragma unroll
             for (int p = 0; p < N / 2; p++) {
@@ -261,18 +270,18 @@ __device__ __forceinline__ void op_dense1(Cx<T> (&x)[Lay<T>::N], const uint4 *pa
 }
 
 template <typename T, int KIND>
-__device__ __forceinline__ void op_group1(Cx<T> (&x)[Lay<T>::N], const uint4 *pay, uint32_t slots, uint32_t emask) {
+__device__ __forceinline__ void op_group1(Cx<T> (&x)[Lay<T>::N], const ProgParam &pp, int pay, uint32_t slots, uint32_t emask) {
     constexpr int NU = (sizeof(T) == 4) ? (KIND == 0 ? 4 : KIND == 2 ? 2 : 1) : (KIND == 0 ? 4 : 2);   // units per matrix
-    if (slots & 1u) { op_dense1<T, 0, KIND>(x, pay, emask); pay += NU; }
-    if (slots & 2u) { op_dense1<T, 1, KIND>(x, pay, emask); pay += NU; }
-    if (slots & 4u) { op_dense1<T, 2, KIND>(x, pay, emask); pay += NU; }
-    if (slots & 8u) { op_dense1<T, 3, KIND>(x, pay, emask); pay += NU; }
-    if (slots & 16u) { op_dense1<T, 4, KIND>(x, pay, emask); }
+    if (slots & 1u) { op_dense1<T, 0, KIND>(x, pp, pay, emask); pay += NU; }
+    if (slots & 2u) { op_dense1<T, 1, KIND>(x, pp, pay, emask); pay += NU; }
+    if (slots & 4u) { op_dense1<T, 2, KIND>(x, pp, pay, emask); pay += NU; }
+    if (slots & 8u) { op_dense1<T, 3, KIND>(x, pp, pay, emask); pay += NU; }
+    if (slots & 16u) { op_dense1<T, 4, KIND>(x, pp, pay, emask); }
 }
 
 // two-target gate: matrix-index bit 0 <-> slot A, bit 1 <-> slot B (A < B)
 template <typename T, int A, int B>
-__device__ __forceinline__ void dense2_group(Cx<T> (&x)[Lay<T>::N], const uint4 *pay, int e0) {
+__device__ __forceinline__ void dense2_group(Cx<T> (&x)[Lay<T>::N], const ProgParam &pp, int pay, int e0) {
     constexpr int RU = 8 * sizeof(T) / 16;           // units per matrix row (4 complex)
     Cx<T> s[4], y[4];
 #pragma unroll
@@ -281,7 +290,7 @@ __device__ __forceinline__ void dense2_group(Cx<T> (&x)[Lay<T>::N], const uint4 
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             float g[16];                                  // row i: {gr, gr, -gi, gi} x 4
-            load_units<4>(pay + i * 4, g);
+            load_units<4>(pp, pay + i * 4, g);
             u64 acc = f2_cmul(f2_pack(g[0], g[1]), f2_pack(g[2], g[3]), s[0]);
 #pragma unroll
             for (int j = 1; j < 4; j++)
@@ -295,7 +304,7 @@ __device__ __forceinline__ void dense2_group(Cx<T> (&x)[Lay<T>::N], const uint4 
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         T g[8];
-        load_units<RU>(pay + i * RU, g);
+        load_units<RU>(pp, pay + i * RU, g);
         T ar = g[0] * s[0].re, ai = g[0] * s[0].im;
         ar = fma(-g[1], s[0].im, ar); ai = fma(g[1], s[0].re, ai);
 #pragma unroll
@@ -307,18 +316,18 @@ __device__ __forceinline__ void dense2_group(Cx<T> (&x)[Lay<T>::N], const uint4 
 }
 
 template <typename T, int A, int B>
-__device__ __forceinline__ void op_dense2(Cx<T> (&x)[Lay<T>::N], const uint4 *pay, uint32_t emask) {
+__device__ __forceinline__ void op_dense2(Cx<T> (&x)[Lay<T>::N], const ProgParam &pp, int pay, uint32_t emask) {
     constexpr int N = Lay<T>::N;
     if constexpr (B < Lay<T>::J) {
         if (emask == (N == 32 ? 0xffffffffu : 0xffffu)) {
 #pragma unroll
-            for (int p = 0; p < N / 4; p++) dense2_group<T, A, B>(x, pay, insert0(insert0(p, A), B));
+            for (int p = 0; p < N / 4; p++) dense2_group<T, A, B>(x, pp, pay, insert0(insert0(p, A), B));
         } else {
 #pragma unroll
             for (int p = 0; p < N / 4; p++) {
                 const int e0 = insert0(insert0(p, A), B);
                 if (!((emask >> e0) & 1u)) continue;
-                dense2_group<T, A, B>(x, pay, e0);
+                dense2_group<T, A, B>(x, pp, pay, e0);
             }
         }
     }
@@ -327,7 +336,7 @@ __device__ __forceinline__ void op_dense2(Cx<T> (&x)[Lay<T>::N], const uint4 *pa
 // two-target gate with a REAL matrix (RY RY CZ RY RY on a pair, products of Hadamards and CZ, ...):
 // re and im parts transform separately, 8 multiply-adds per amplitude instead of 16
 template <typename T, int A, int B>
-__device__ __forceinline__ void dense2r_group(Cx<T> (&x)[Lay<T>::N], const uint4 *pay, int e0) {
+__device__ __forceinline__ void dense2r_group(Cx<T> (&x)[Lay<T>::N], const ProgParam &pp, int pay, int e0) {
     Cx<T> s[4], y[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) s[j] = x[e0 | ((j & 1) << A) | ((j >> 1) << B)];
@@ -335,7 +344,7 @@ __device__ __forceinline__ void dense2r_group(Cx<T> (&x)[Lay<T>::N], const uint4
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             float g[4];                                   // row i
-            load_units<1>(pay + i, g);
+            load_units<1>(pp, pay + i, g);
             u64 acc = f2_mul(f2_splat(g[0]), f2_of(s[0]));
 #pragma unroll
             for (int j = 1; j < 4; j++) acc = f2_fma(f2_splat(g[j]), f2_of(s[j]), acc);
@@ -345,7 +354,7 @@ __device__ __forceinline__ void dense2r_group(Cx<T> (&x)[Lay<T>::N], const uint4
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             T g[4];
-            load_units<2>(pay + 2 * i, g);
+            load_units<2>(pp, pay + 2 * i, g);
             T ar = g[0] * s[0].re, ai = g[0] * s[0].im;
 #pragma unroll
             for (int j = 1; j < 4; j++) { ar = fma(g[j], s[j].re, ar); ai = fma(g[j], s[j].im, ai); }
@@ -357,18 +366,18 @@ __device__ __forceinline__ void dense2r_group(Cx<T> (&x)[Lay<T>::N], const uint4
 }
 
 template <typename T, int A, int B>
-__device__ __forceinline__ void op_dense2r(Cx<T> (&x)[Lay<T>::N], const uint4 *pay, uint32_t emask) {
+__device__ __forceinline__ void op_dense2r(Cx<T> (&x)[Lay<T>::N], const ProgParam &pp, int pay, uint32_t emask) {
     constexpr int N = Lay<T>::N;
     if constexpr (B < Lay<T>::J) {
         if (emask == (N == 32 ? 0xffffffffu : 0xffffu)) {
 #pragma unroll
-            for (int p = 0; p < N / 4; p++) dense2r_group<T, A, B>(x, pay, insert0(insert0(p, A), B));
+            for (int p = 0; p < N / 4; p++) dense2r_group<T, A, B>(x, pp, pay, insert0(insert0(p, A), B));
         } else {
 #pragma unroll
             for (int p = 0; p < N / 4; p++) {
                 const int e0 = insert0(insert0(p, A), B);
                 if (!((emask >> e0) & 1u)) continue;
-                dense2r_group<T, A, B>(x, pay, e0);
+                dense2r_group<T, A, B>(x, pp, pay, e0);
             }
         }
     }
@@ -507,43 +516,59 @@ __device__ __forceinline__ Cx<T> cx_mul(const Cx<T> &a, const Cx<T> &b) {
 }
 
 // Fused diagonal: every diagonal gate waiting at this point of the round whose other bits are all
-// inside the tile (-> G, one host-made factor per 16-byte unit and thread, laid out [unit][thread]:
-// coalesced, L1/L2 resident) or all outside it (-> F, one factor per element and tile, made at tile
-// start) in ONE op: x[e] *= G[unit(e)][tid] * F[e].  `um`: the units that hold a non-trivial factor.
-template <typename T, bool HASF>
-__device__ __forceinline__ void op_diagf(Cx<T> (&x)[Lay<T>::N], const Cx<T> *__restrict__ gp, int stride, uint32_t um,
-                                         bool has_g, const Cx<T> *fp) {
+// inside the tile (-> G, one host-made factor per 16-byte unit and thread, laid out [thread][unit]:
+// a thread's 16 units are 256 contiguous bytes, every load has an immediate offset; L1/L2 resident)
+// or all outside it (-> F, one factor per element and tile, made at tile start) in ONE op:
+// x[e] *= G[tid][unit(e)] * F[e].  `um`: the units that hold a non-trivial factor (FULL: all).
+template <typename T, bool HASF, bool FULL>
+__device__ __forceinline__ void op_diagf(Cx<T> (&x)[Lay<T>::N], const Cx<T> *__restrict__ gp, uint32_t um, bool has_g,
+                                         const Cx<T> *fp) {
+    constexpr int UPE = sizeof(T) == 8 ? 1 : 2;    // elements per unit
 #pragma unroll
     for (int c = 0; c < 16; c += 8) {
-        if constexpr (sizeof(T) == 8) {
-            Cx<T> z[8];
+        Cx<T> z[8 * UPE];
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
+        for (int k = 0; k < 8; k++) {
+            const bool on = FULL || ((um >> (c + k)) & 1u);
+            if constexpr (sizeof(T) == 8) {
                 z[k].re = T(1); z[k].im = T(0);
-                if (has_g && ((um >> (c + k)) & 1u)) z[k] = ldg_cx(gp + (c + k) * stride);
+                if (has_g && on) z[k] = ldg_cx(gp + (c + k));
+            } else {
+                float4 q = make_float4(1.f, 0.f, 1.f, 0.f);
+                if (has_g && on) q = ldg_f4(gp + 2 * (c + k));
+                z[2 * k].re = q.x; z[2 * k].im = q.y; z[2 * k + 1].re = q.z; z[2 * k + 1].im = q.w;
             }
+        }
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
-                if (!((um >> (c + k)) & 1u)) continue;
-                if (HASF) z[k] = cx_mul<T>(z[k], fp[c + k]);
-                cmul_inplace<T>(x[c + k], z[k].re, z[k].im);
+        for (int k = 0; k < 8; k++) {
+            if (!FULL && !((um >> (c + k)) & 1u)) continue;
+#pragma unroll
+            for (int j = 0; j < UPE; j++) {
+                const int e = (c + k) * UPE + j;
+                Cx<T> w = z[k * UPE + j];
+                if (HASF) w = cx_mul<T>(w, fp[e]);
+                cmul_inplace<T>(x[e], w.re, w.im);
             }
+        }
+    }
+}
+
+// Constant diagonal: factors that depend on the register bits only (the phases between the H
+// gates of a QFT round, CZ / CU1 inside a register block): one complex constant per selected
+// 16-byte unit, read from the program image as uniform operands -- no memory traffic at all.
+template <typename T>
+__device__ __forceinline__ void op_diagc(Cx<T> (&x)[Lay<T>::N], const ProgParam &pp, int pay, uint32_t um) {
+    constexpr int UPE = sizeof(T) == 8 ? 1 : 2;
+#pragma unroll
+    for (int u = 0; u < 16; u++) {
+        if (!((um >> u) & 1u)) continue;
+        const uint4 q = pp.u[pay];
+        pay++;
+        if constexpr (sizeof(T) == 8) {
+            cmul_inplace<T>(x[u], __hiloint2double(int(q.y), int(q.x)), __hiloint2double(int(q.w), int(q.z)));
         } else {
-            float4 z[8];
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-                z[k] = make_float4(1.f, 0.f, 1.f, 0.f);
-                if (has_g && ((um >> (c + k)) & 1u)) z[k] = ldg_f4(gp + 2 * (c + k) * stride);
-            }
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-                if (!((um >> (c + k)) & 1u)) continue;
-                Cx<T> z0, z1;
-                z0.re = z[k].x; z0.im = z[k].y; z1.re = z[k].z; z1.im = z[k].w;
-                if (HASF) { z0 = cx_mul<T>(z0, fp[2 * (c + k)]); z1 = cx_mul<T>(z1, fp[2 * (c + k) + 1]); }
-                cmul_inplace<T>(x[2 * (c + k)], z0.re, z0.im);
-                cmul_inplace<T>(x[2 * (c + k) + 1], z1.re, z1.im);
-            }
+            cmul_inplace<T>(x[2 * u], __uint_as_float(q.x), __uint_as_float(q.y));
+            cmul_inplace<T>(x[2 * u + 1], __uint_as_float(q.z), __uint_as_float(q.w));
         }
     }
 }
@@ -598,8 +623,8 @@ __device__ __forceinline__ int32_t outer_value(const uint4 *outers, int m, int64
 
 template <typename T>
 __global__ void __launch_bounds__(kThreads, 2)
-k_pass(Cx<T> *__restrict__ state, const __grid_constant__ PassGeom pg, const uint4 *__restrict__ blob,
-       const Cx<T> *__restrict__ tables) {
+k_pass(Cx<T> *__restrict__ state, const __grid_constant__ PassGeom pg, const Cx<T> *__restrict__ tables,
+       const __grid_constant__ ProgParam pp) {
     constexpr int N = Lay<T>::N;
     constexpr int VS = Lay<T>::VS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -611,28 +636,30 @@ k_pass(Cx<T> *__restrict__ state, const __grid_constant__ PassGeom pg, const uin
     const int rvmask = (1 << rv) - 1;
     uint4 *const tilev = reinterpret_cast<uint4 *>(smem_raw);
     uint4 *const prog = tilev + nvec;
-    uint4 *const s_H = prog + pg.blob_units;                                        // one 16-byte slot per factor
+    uint4 *const s_H = prog + pg.prefix_units;                                      // one 16-byte slot per factor
     Cx<T> *const s_F = reinterpret_cast<Cx<T> *>(s_H + pg.nH);                      // N factors per fused diagonal
     int64_t *const s_runoff = reinterpret_cast<int64_t *>(s_F + pg.nF * N);         // in vectors
     int32_t *const s_outer = reinterpret_cast<int32_t *>(s_runoff + (1 << pg.nh));
     uint4 *const gvec = reinterpret_cast<uint4 *>(state);
 
     const int nthr = int(blockDim.x);
-    for (int i = tid; i < pg.blob_units; i += nthr) prog[i] = __ldg(blob + i);
+    // the descriptors that threads index individually (outer slots, H and F entries) live in
+    // shared memory; the op stream stays in the constant bank
+    for (int i = tid; i < pg.prefix_units; i += nthr) prog[i] = pp.u[i];
     for (int run = tid; run < (1 << pg.nh); run += nthr) {
         int64_t off = 0;
         for (int b = 0; b < pg.nh; b++) off |= int64_t((run >> b) & 1) << (pg.hibit[b] - VS);
         s_runoff[run] = off;
     }
     __syncthreads();
-    const uint4 hdr = prog[0];
+    const uint4 hdr = pp.u[0], hdr1 = pp.u[1];
     const int nrounds = int(hdr.x), nouter = int(hdr.y);
-    const uint4 *const rounds = prog + hdr.z;
+    const int rounds = int(hdr.z);                 // unit index of the round descriptors (constant bank)
     const uint4 *const outers = prog + hdr.w;
-    const int nH = int(prog[1].x);
-    const uint4 *const hents = prog + prog[1].y;
-    const int nF = int(prog[1].z);
-    const uint4 *const fents = prog + prog[1].w;
+    const int nH = int(hdr1.x);
+    const uint4 *const hents = prog + hdr1.y;
+    const int nF = int(hdr1.z);
+    const uint4 *const fents = prog + hdr1.w;
 
     // (the launch uses exactly one thread per 16 vectors of the tile: every thread is live)
     const bool fast_io = nthr >= 8 && nthr >= (1 << rv) && nvec == 16 * nthr;   // 16 vectors per thread
@@ -703,7 +730,7 @@ k_pass(Cx<T> *__restrict__ state, const __grid_constant__ PassGeom pg, const uin
         // ---- rounds
 #pragma unroll 1
         for (int rd = 0; rd < nrounds; rd++) {
-            const uint4 r0 = rounds[3 * rd], r1 = rounds[3 * rd + 1], r2 = rounds[3 * rd + 2];
+            const uint4 r0 = pp.u[rounds + 3 * rd], r1 = pp.u[rounds + 3 * rd + 1], r2 = pp.u[rounds + 3 * rd + 2];
             {
                 uint32_t vd[4] = {r0.z & 0xffffu, r0.z >> 16, r0.w & 0xffffu, r0.w >> 16};
                 const uint32_t tdw[4] = {r1.x, r1.y, r1.z, r1.w};
@@ -733,17 +760,17 @@ k_pass(Cx<T> *__restrict__ state, const __grid_constant__ PassGeom pg, const uin
                 // The op loop has warp-uniform control flow only: a thread whose predicate fails
                 // (control bit outside the registers is 0, outer control not satisfied) runs the
                 // same op with an empty element mask / a unit phase instead of branching around it.
-                const uint4 *op = prog + r0.x;
-                const uint4 *const op_end = op + r0.y;   // r0.y = units of this round's op stream
+                int op = int(r0.x);                      // unit index into the program image
+                const int op_end = op + int(r0.y);       // r0.y = units of this round's op stream
 #pragma unroll 1
                 while (op != op_end) {
-                    uint4 h0 = op[0], h1 = op[1];
-                    const uint4 *pay = op + 2;
-                    op += h0.x >> 16;
+                    uint4 h0 = pp.u[op], h1 = pp.u[op + 1];
+                    int pay = op + 2;
+                    op += int(h0.x >> 16);
                     const uint32_t code = h0.x & 0xffffu;
                     uint32_t emask = h0.w;
                     int oi = 0;
-                    if (code != C_PHASE && code != C_DIAGF && (h0.z != 0u || (h0.y & 0xffffu) != 0xffffu)) {   // predicated op
+                    if (code != C_PHASE && code != C_DIAGF && code != C_DIAGC && (h0.z != 0u || (h0.y & 0xffffu) != 0xffffu)) {   // predicated op
                         const uint32_t oslot = h0.y & 0xffffu, tmask = h0.z;
                         bool ok = (base & tmask) == tmask;
                         if (oslot != 0xffffu) {
@@ -755,12 +782,12 @@ k_pass(Cx<T> *__restrict__ state, const __grid_constant__ PassGeom pg, const uin
                     }
                     switch (code) {
 #define QJ_P1(A) op_perm1<T, A>(x, emask)
-#define QJ_D2(A, B) op_dense2<T, A, B>(x, pay, emask)
+#define QJ_D2(A, B) op_dense2<T, A, B>(x, pp, pay, emask)
 #define QJ_P2(A, B) op_perm2<T, A, B>(x, emask)
-#define QJ_D2R(A, B) op_dense2r<T, A, B>(x, pay, emask)
-                        case C_GROUP1C: op_group1<T, 0>(x, pay, h0.y >> 16, emask); break;
-                        case C_GROUP1R: op_group1<T, 1>(x, pay, h0.y >> 16, emask); break;
-                        case C_GROUP1X: op_group1<T, 2>(x, pay, h0.y >> 16, emask); break;
+#define QJ_D2R(A, B) op_dense2r<T, A, B>(x, pp, pay, emask)
+                        case C_GROUP1C: op_group1<T, 0>(x, pp, pay, h0.y >> 16, emask); break;
+                        case C_GROUP1R: op_group1<T, 1>(x, pp, pay, h0.y >> 16, emask); break;
+                        case C_GROUP1X: op_group1<T, 2>(x, pp, pay, h0.y >> 16, emask); break;
                         QJ_SLOT_CASES(C_PERM1, QJ_P1)
                         QJ_PAIR_CASES(C_DENSE2, QJ_D2)
                         QJ_PAIR_CASES(C_PERM2, QJ_P2)
@@ -777,12 +804,12 @@ k_pass(Cx<T> *__restrict__ state, const __grid_constant__ PassGeom pg, const uin
                           gcur.re = T(1); gcur.im = T(0);
                           if (h1.x != 0xffffffffu) gcur = ldg_cx(tables + h1.x + tid);
                           for (;;) {
-                            const bool more = op != op_end && (op[0].x & 0xffffu) == uint32_t(C_PHASE);
+                            const bool more = op != op_end && (pp.u[op].x & 0xffffu) == uint32_t(C_PHASE);
                             uint4 n0 = h0, n1 = h1;
                             Cx<T> gnext;
                             gnext.re = T(1); gnext.im = T(0);
                             if (more) {
-                                n0 = op[0]; n1 = op[1];
+                                n0 = pp.u[op]; n1 = pp.u[op + 1];
                                 if (n1.x != 0xffffffffu) gnext = ldg_cx(tables + n1.x + tid);
                             }
                             // h0.y = ntab | sel << 16, h0.z = all-sign flag; descriptors: 2 (<= 5 fields)
@@ -790,7 +817,7 @@ k_pass(Cx<T> *__restrict__ state, const __grid_constant__ PassGeom pg, const uin
                             const int ntab = int(h0.y & 0xffffu);
                             const uint32_t sel = h0.y >> 16;
                             const bool allsign = h0.z != 0u;
-                            const uint4 *d = pay;
+                            int d = pay;
                             Cx<T> ph;
                             ph.re = T(1); ph.im = T(0);
                             uint32_t sg = 0;
@@ -823,10 +850,10 @@ k_pass(Cx<T> *__restrict__ state, const __grid_constant__ PassGeom pg, const uin
                                 for (int k = 0; k < KB; k++) {
                                     z[k].re = T(1); z[k].im = T(0);
                                     if (t0 + k < ntab) {
-                                        const uint4 d0 = d[0], d1 = d[1];
+                                        const uint4 d0 = pp.u[d], d1 = pp.u[d + 1];
                                         const int nf = int(d0.y & 0xffffu);
                                         const uint32_t osl = d0.y >> 16;
-                                        const uint4 *const dx = d + 2;
+                                        const int dx = d + 2;
                                         d += (nf > 5) ? 3 : 2;
                                         int idx = 0;
                                         bool ok = (base & d0.z) == d0.z;     // tile-local control outside the registers
@@ -842,7 +869,7 @@ k_pass(Cx<T> *__restrict__ state, const __grid_constant__ PassGeom pg, const uin
                                                 if (nf > 3) idx |= field_of(base, d1.z);
                                                 if (nf > 4) idx |= field_of(base, d1.w);
                                                 if (nf > 5) {
-                                                    const uint4 d2 = dx[0];
+                                                    const uint4 d2 = pp.u[dx];
                                                     idx |= field_of(base, d2.x);
                                                     if (nf > 6) idx |= field_of(base, d2.y);
                                                     if (nf > 7) idx |= field_of(base, d2.z);
@@ -873,20 +900,27 @@ k_pass(Cx<T> *__restrict__ state, const __grid_constant__ PassGeom pg, const uin
                             if (!more) break;
                             h0 = n0; h1 = n1;
                             pay = op + 2;
-                            op += n0.x >> 16;
+                            op += int(n0.x >> 16);
                             emask = n0.w;
                             gcur = gnext;
                           }
                         } break;
                         case C_DIAGF: {   // h0.y = F index (0xffff: none) | has_g << 16, h0.w = unit mask, h1.x = G
                             const uint32_t fidx = h0.y & 0xffffu;
-                            const Cx<T> *const gp = tables + h1.x + tid * (VS ? 2 : 1);
-                            if (fidx != 0xffffu) op_diagf<T, true>(x, gp, nthr, h0.w, (h0.y >> 16) != 0u, s_F + fidx * N);
-                            else op_diagf<T, false>(x, gp, nthr, h0.w, true, nullptr);
+                            const Cx<T> *const gp = tables + h1.x + tid * (VS ? 32 : 16);
+                            const bool full = h0.w == 0xffffu;
+                            if (fidx != 0xffffu) {
+                                if (full) op_diagf<T, true, true>(x, gp, h0.w, (h0.y >> 16) != 0u, s_F + fidx * N);
+                                else op_diagf<T, true, false>(x, gp, h0.w, (h0.y >> 16) != 0u, s_F + fidx * N);
+                            } else {
+                                if (full) op_diagf<T, false, true>(x, gp, h0.w, true, nullptr);
+                                else op_diagf<T, false, false>(x, gp, h0.w, true, nullptr);
+                            }
                         } break;
+                        case C_DIAGC: op_diagc<T>(x, pp, pay, h0.w); break;
                         default: {  // C_DIAGN: table index = outer part | fields of the base | element part
                             const int nf = int(h0.y >> 16);
-                            const uint4 f = pay[0], w = pay[1];
+                            const uint4 f = pp.u[pay], w = pp.u[pay + 1];
                             int idxb = oi;
                             if (nf > 0) idxb |= field_of(base, h1.y);
                             if (nf > 1) idxb |= field_of(base, h1.z);
@@ -1047,12 +1081,12 @@ struct qj_program {
     int nqubits = 0;
     struct Launch {
         qj::PassGeom geom;
-        int64_t blob_off = 0;   // units into d_blob
+        int64_t blob_off = 0;   // units into h_blob
         size_t smem = 0;
         int nrounds = 0, nops = 0;
     };
     std::vector<Launch> launches;
-    void *d_blob = nullptr;
+    std::vector<qj::ProgParam> images;   // one kernel-parameter image per launch (host memory)
     void *d_tables = nullptr;
     int64_t total_mops = 0, total_rounds = 0;
 };
@@ -1118,6 +1152,9 @@ static int program_build(qj_handle *h, int dtype, int nqubits, const qj_pass_des
         int r = 0;
         while (r < T && pd.local_bits[r] == r) r++;
         if (r < 1) return bail("pass: the tile must contain index bit 0");
+        // the tile IO moves one contiguous run per group of threads: a run longer than a 16th of
+        // the tile is split (its upper bits are addressed like arbitrary high bits)
+        r = std::max(1, std::min(r, T - 4));
         if (T - r > kMaxHiBits) return bail("pass: too many local bits above the contiguous run");
         if (pd.first_round < 0 || pd.nrounds < 0 || pd.first_round + pd.nrounds > nrounds_in)
             return bail("pass: round range out of bounds");
@@ -1163,12 +1200,13 @@ static int program_build(qj_handle *h, int dtype, int nqubits, const qj_pass_des
             qj_program::Launch L;
             L.geom = geo;
             L.geom.blob_units = int(img.size());
+            L.geom.prefix_units = int(off_ops);
             L.blob_off = int64_t(blob_all.size());
             L.nrounds = launch_rounds;
             L.nops = launch_ops;
             L.geom.nH = int(h_units.size() / 4);
             L.geom.nF = int(f_dir.size());
-            L.smem = (size_t(1) << Tv) * 16 + img.size() * 16 + (h_units.size() / 4) * 16 + f_dir.size() * 256 +
+            L.smem = (size_t(1) << Tv) * 16 + size_t(off_ops) * 16 + (h_units.size() / 4) * 16 + f_dir.size() * 256 +
                      (size_t(8) << geo.nh) + (outer_units.size() / 2) * 4 + 16;
             prog->launches.push_back(L);
             blob_all.insert(blob_all.end(), img.begin(), img.end());
@@ -1297,9 +1335,58 @@ static int program_build(qj_handle *h, int dtype, int nqubits, const qj_pass_des
             };
             auto flush_pending = [&]() {
                 if (!pending.empty()) group_run.clear();
-                // ---- fused diagonal: when several groups (different element sets) wait here, the
-                // thread-only slices become ONE per-unit, per-thread factor array and the outer-only
-                // slices one per-element, per-tile factor array: one dispatch, one multiply per element
+                // ---- fused diagonals.  (1) Slices whose factor depends on the register bits only
+                // (thread-only class with a one-entry table, no thread predicate) become ONE constant
+                // diagonal op: per-unit constants in the payload, uniform operands, no loads.
+                // (2) When several groups (different element sets) still wait, the thread-only slices
+                // become ONE per-thread, per-unit factor array and the outer-only slices one
+                // per-element, per-tile factor array: one dispatch, one multiply per element.
+                auto thread_base = [&](int t) {
+                    uint32_t base = 0;
+                    for (size_t kb = 0; kb < tq.size(); kb++) if ((t >> kb) & 1) base |= 1u << (tq[kb] + VS);
+                    return base;
+                };
+                if (fuse_min > 0) {
+                    std::vector<PendingSlice> keep;
+                    std::vector<const PendingSlice *> cm;
+                    bool all_sign = true;
+                    for (const PendingSlice &ps : pending) {
+                        if (ps.cls == 0 && ps.tmask == 0 && ps.nf == 0) {
+                            cm.push_back(&ps);
+                            all_sign = all_sign && ps.sign;
+                        } else {
+                            keep.push_back(ps);
+                        }
+                    }
+                    if (!cm.empty() && !all_sign) {          // (pure sign flips stay phase groups: no arithmetic)
+                        std::vector<cd> fac(size_t(N), cd(1.0));
+                        uint32_t emu = 0;
+                        for (const PendingSlice *ps : cm) {
+                            emu |= ps->emask;
+                            for (int e = 0; e < N; e++) if ((ps->emask >> e) & 1u) fac[size_t(e)] *= ps->host[0];
+                        }
+                        uint32_t um = 0;
+                        std::vector<double> sc;
+                        for (int u = 0; u < 16; u++) {
+                            if (!((emu >> (u << VS)) & (VS ? 3u : 1u))) continue;
+                            um |= 1u << u;
+                            for (int j = 0; j < (1 << VS); j++) {
+                                const cd z = fac[size_t((u << VS) + j)];
+                                sc.push_back(z.real()); sc.push_back(z.imag());
+                            }
+                        }
+                        std::vector<Unit> payload;
+                        enc.push_scalars(payload, sc);
+                        Unit h0, h1;
+                        memset(&h1, 0, sizeof(h1));
+                        h0.w[0] = uint32_t(C_DIAGC) | (uint32_t(2 + payload.size()) << 16);
+                        h0.w[1] = 0xffffu; h0.w[2] = 0; h0.w[3] = um;
+                        r_ops.push_back(h0); r_ops.push_back(h1);
+                        r_ops.insert(r_ops.end(), payload.begin(), payload.end());
+                        r_nops++;
+                        pending = keep;
+                    }
+                }
                 {
                     std::vector<uint32_t> masks;
                     bool any_f = false;
@@ -1322,21 +1409,20 @@ static int program_build(qj_handle *h, int dtype, int nqubits, const qj_pass_des
                         uint32_t um = 0;
                         for (int u = 0; u < 16; u++)
                             if ((emu >> (u << VS)) & (VS ? 3u : 1u)) um |= 1u << u;
+                        if (__builtin_popcount(um) >= 12) um = 0xffffu;   // nearly full: the mask-free code path (factor 1 elsewhere)
                         uint32_t g_off = 0xffffffffu;
                         if (!gm.empty()) {
                             const int upe = 1 << VS;   // elements per 16-byte unit
-                            std::vector<cd> G(size_t(16) * size_t(nthr_round) * size_t(upe), cd(1.0));
+                            std::vector<cd> G(size_t(16) * size_t(nthr_round) * size_t(upe), cd(1.0));   // [thread][unit][element]
                             for (const PendingSlice *ps : gm) {
                                 for (int t = 0; t < nthr_round; t++) {
-                                    uint32_t base = 0;
-                                    for (size_t kb = 0; kb < tq.size(); kb++) if ((t >> kb) & 1) base |= 1u << (tq[kb] + VS);
+                                    const uint32_t base = thread_base(t);
                                     if ((base & ps->tmask) != ps->tmask) continue;
                                     uint32_t idx = 0;
                                     for (int f = 0; f < ps->nf; f++) idx |= host_field(base, ps->fields[f]);
                                     const cd z = ps->host[idx];
                                     for (int e = 0; e < N; e++)
-                                        if ((ps->emask >> e) & 1u)
-                                            G[(size_t(e >> VS) * size_t(nthr_round) + size_t(t)) * size_t(upe) + size_t(e & (upe - 1))] *= z;
+                                        if ((ps->emask >> e) & 1u) G[size_t(t) * size_t(N) + size_t(e)] *= z;
                                 }
                             }
                             if (VS && ((enc.tables.size() / enc.esz) & 1)) enc.push_table(std::vector<cd>(1, cd(1.0)));   // 16-byte alignment
@@ -1761,15 +1847,20 @@ static int program_build(qj_handle *h, int dtype, int nqubits, const qj_pass_des
         delete prog;
         return QJ_OK;
     }
-    cudaSetDevice(h->device);
+    qj::DeviceGuard device_guard(h);
     auto upload = [&](void **dst, const void *src, size_t bytes) -> cudaError_t {
         if (bytes == 0) bytes = 16;   // never hand a null table pointer to the kernel
         cudaError_t e = cudaMalloc(dst, bytes);
         if (e != cudaSuccess || src == nullptr) return e;
         return cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, h->stream);
     };
-    cudaError_t e = upload(&prog->d_blob, blob_all.empty() ? nullptr : blob_all.data(), blob_all.size() * 16);
-    if (e == cudaSuccess) e = upload(&prog->d_tables, enc.tables.empty() ? nullptr : enc.tables.data(), enc.tables.size());
+    prog->images.resize(prog->launches.size());
+    for (size_t li = 0; li < prog->launches.size(); li++) {
+        const qj_program::Launch &L = prog->launches[li];
+        memset(&prog->images[li], 0, sizeof(ProgParam));
+        memcpy(prog->images[li].u, blob_all.data() + L.blob_off, size_t(L.geom.blob_units) * 16);
+    }
+    cudaError_t e = upload(&prog->d_tables, enc.tables.empty() ? nullptr : enc.tables.data(), enc.tables.size());
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);  // host vectors die with this frame
     if (e != cudaSuccess) {
         qj_program_destroy(h, prog);
@@ -1783,6 +1874,7 @@ extern "C" int qj_program_create(qj_handle *h, int dtype, int nqubits, const qj_
                                  int npasses, const qj_round_desc *rounds_in, int64_t nrounds_in,
                                  const qj_op_desc *ops, int64_t nops, const void *data, int64_t ndata,
                                  qj_program **out) {
+    qj::DeviceGuard device_guard(h);
     QJ_REQUIRE(h && out, "null argument");
     return program_build(h, dtype, nqubits, passes, npasses, rounds_in, nrounds_in, ops, nops, data, ndata, out, nullptr);
 }
@@ -1834,12 +1926,9 @@ extern "C" int qj_program_image_destroy(qj_program_image *img) {
 }
 
 extern "C" int qj_program_destroy(qj_handle *h, qj_program *p) {
+    qj::DeviceGuard device_guard(h);
     if (!p) return QJ_OK;
-    if (h) {
-        cudaSetDevice(h->device);
-        cudaStreamSynchronize(h->stream);
-    }
-    cudaFree(p->d_blob);
+    if (h) cudaStreamSynchronize(h->stream);   // (without a handle cudaFree synchronises the device by itself)
     cudaFree(p->d_tables);
     delete p;
     return QJ_OK;
@@ -1855,11 +1944,12 @@ extern "C" int qj_program_stats(const qj_program *p, int64_t *nlaunches, int64_t
 
 namespace {
 template <typename T>
-int launch_pass(qj_handle *h, const qj_program *p, void *state, const qj_program::Launch &L) {
-    static bool configured = false;
-    if (!configured) {
+int launch_pass(qj_handle *h, const qj_program *p, void *state, int li) {
+    const qj_program::Launch &L = p->launches[li];
+    static bool configured[kMaxDevices] = {false};   // the attribute is per device, not per process
+    if (!configured[h->device]) {
         QJ_CUDA_OK(cudaFuncSetAttribute(k_pass<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 << 10));
-        configured = true;
+        configured[h->device] = true;
     }
     // one thread per 16 vectors of the tile (at most 256); 128 registers per thread allow 512
     // resident threads per SM: two 64 KiB tiles or four 32 KiB tiles in different phases
@@ -1869,8 +1959,7 @@ int launch_pass(qj_handle *h, const qj_program *p, void *state, const qj_program
     const int per_sm = std::max(1, std::min(by_smem, 512 / threads));
     const unsigned grid = (unsigned)std::min<int64_t>(L.geom.ntiles, int64_t(h->sm_count) * per_sm);
     k_pass<T><<<grid, threads, L.smem, h->stream>>>(
-        reinterpret_cast<Cx<T> *>(state), L.geom, reinterpret_cast<const uint4 *>(p->d_blob) + L.blob_off,
-        reinterpret_cast<const Cx<T> *>(p->d_tables));
+        reinterpret_cast<Cx<T> *>(state), L.geom, reinterpret_cast<const Cx<T> *>(p->d_tables), p->images[li]);
     h->launches++;
     QJ_CUDA_OK(cudaGetLastError());
     return QJ_OK;
@@ -1878,8 +1967,7 @@ int launch_pass(qj_handle *h, const qj_program *p, void *state, const qj_program
 
 int run_launches(qj_handle *h, const qj_program *p, void *state, int first, int count) {
     for (int li = first; li < first + count; li++) {
-        const qj_program::Launch &L = p->launches[li];
-        const int rc = (p->dtype == QJ_C128) ? launch_pass<double>(h, p, state, L) : launch_pass<float>(h, p, state, L);
+        const int rc = (p->dtype == QJ_C128) ? launch_pass<double>(h, p, state, li) : launch_pass<float>(h, p, state, li);
         if (rc) return rc;
     }
     return QJ_OK;
@@ -1887,12 +1975,14 @@ int run_launches(qj_handle *h, const qj_program *p, void *state, int first, int 
 }  // namespace
 
 extern "C" int qj_program_run(qj_handle *h, const qj_program *p, void *state) {
+    qj::DeviceGuard device_guard(h);
     QJ_REQUIRE(h && p && state, "null argument");
     QJ_REQUIRE((reinterpret_cast<uintptr_t>(state) & 15) == 0, "state must be 16-byte aligned");
     return run_launches(h, p, state, 0, (int)p->launches.size());
 }
 
 extern "C" int qj_program_run_launch(qj_handle *h, const qj_program *p, void *state, int launch) {
+    qj::DeviceGuard device_guard(h);
     QJ_REQUIRE(h && p && state, "null argument");
     QJ_REQUIRE(launch >= 0 && launch < (int)p->launches.size(), "launch index out of range");
     return run_launches(h, p, state, launch, 1);

@@ -323,11 +323,11 @@ int launch_tile_ks(qj_handle *h, const GateCall &c, const TilePlan &p) {
     constexpr int NE = 1 << K;
     CMat<T, NE> mat;
     memcpy(mat.v, c.gate, sizeof(mat.v));
-    static bool configured = false;
+    static bool configured[kMaxDevices] = {false};   // the attribute is per device, not per process
     static int per_sm_cached[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (!configured) {
+    if (!configured[h->device]) {
         QJ_CUDA_OK(cudaFuncSetAttribute(k_dense_tile<T, K, SL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 << 10));
-        configured = true;
+        configured[h->device] = true;
     }
     const int slot = std::min<int>(7, int(p.smem >> 15));
     if (per_sm_cached[slot] == 0) {

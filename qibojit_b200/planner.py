@@ -586,6 +586,7 @@ class Program:
         self.run_bits = int(run_bits or DEFAULT_RUN_BITS[self.dtype])
         self.max_diag_bits = min(int(max_diag_bits), _capi.QJ_MAX_DIAG_BITS)
         self.ngates = len(queue)
+        self.closed = False
         self.segments = []       # ('program', handle, npasses) | ('raw', gate)
         self.passes = []         # [(local_bits, [(reg_bits, [PlanOp])])] for inspection
         self.upload_bytes = 0    # host bytes handed to qj_program_create (descriptors + matrices/tables)
@@ -653,8 +654,13 @@ class Program:
         self.passes.extend(passes)
 
     # -- execution
+    def _check_open(self):
+        if getattr(self, "closed", False):
+            raise RuntimeError("this Program was closed (its device image is released): compile the circuit again")
+
     def run(self, state):
         b = self.backend
+        self._check_open()
         if state.numel() != (1 << self.nqubits) or str(state.dtype).replace("torch.", "") != self.dtype:
             raise ValueError("state does not match the program's qubit count / dtype")
         for seg in self.segments:
@@ -671,6 +677,7 @@ class Program:
         from .backends.b200 import GATE_OPS
 
         b = self.backend
+        self._check_open()
         for seg in self.segments:
             if seg[0] == "program":
                 a = ctypes.c_int64()
@@ -749,10 +756,15 @@ class Program:
         return out
 
     def close(self):
+        """Release the device images.  A closed program raises on run() instead of silently
+        returning its input."""
         for seg in self.segments:
             if seg[0] == "program" and seg[1]:
-                self.backend._lib.qj_program_destroy(self.backend._handle(), seg[1])
+                # the library synchronises the creating handle's stream when it is still alive;
+                # a destroyed backend passes None (cudaFree synchronises by itself)
+                self.backend._lib.qj_program_destroy(self.backend._handle_or_none(), seg[1])
         self.segments = []
+        self.closed = True
 
     def __del__(self):
         try:

@@ -16,7 +16,7 @@ import numpy as np
 from qibojit_b200 import _capi, planner
 
 C_GROUP1C, C_GROUP1R, C_GROUP1X, C_PERM1, C_DENSE2, C_PERM2, C_PHASE, C_DIAGN = 0, 1, 2, 3, 8, 18, 28, 29
-C_DENSE2R, C_DIAGF = 30, 40
+C_DENSE2R, C_DIAGF, C_DIAGC = 30, 40, 41
 SEL_ALL, SEL_SLOT, SEL_PAIR, SEL_MASK = 0, 1, 6, 16
 PAIRS = [(0, 1), (0, 2), (1, 2), (0, 3), (1, 3), (2, 3), (0, 4), (1, 4), (2, 4), (3, 4)]
 
@@ -64,6 +64,9 @@ class EncoderBackend:
         self._lib = _EncodeLib()
 
     def _handle(self):
+        return None
+
+    def _handle_or_none(self):
         return None
 
 
@@ -196,7 +199,7 @@ def run_image(image, state):
                     op += units
                     emask = np.full(nthr, int(h0[3]), dtype=np.int64)
                     oi = 0
-                    if code not in (C_PHASE, C_DIAGF) and (int(h0[2]) != 0 or (int(h0[1]) & 0xffff) != 0xffff):
+                    if code not in (C_PHASE, C_DIAGF, C_DIAGC) and (int(h0[2]) != 0 or (int(h0[1]) & 0xffff) != 0xffff):
                         oslot, tmask = int(h0[1]) & 0xffff, int(h0[2])
                         ok = (base & tmask) == tmask
                         if oslot != 0xffff:
@@ -312,11 +315,24 @@ def run_image(image, state):
                                 ee = u * upe + k
                                 z = np.ones(nthr, dtype=np.complex128)
                                 if has_g:
-                                    z = image.tables[int(h1[0]) + (u * nthr + tid) * upe + k]
+                                    z = image.tables[int(h1[0]) + (tid * 16 + u) * upe + k]      # [thread][unit][element]
                                 if fidx != 0xffff:
                                     z = z * s_F[fidx, ee]
                                 x[:, ee] *= z
                         assert units == 2
+                    elif code == C_DIAGC:
+                        um = int(h0[3])
+                        upe = 1 << VS
+                        nun = bin(um).count("1")
+                        assert units == 2 + nun
+                        sc = image.scalars(U[pay:pay + nun]).reshape(nun, -1)     # c128: (re, im); c64: (re, im, re, im)
+                        k = 0
+                        for u in range(16):
+                            if not (um >> u) & 1:
+                                continue
+                            for j in range(upe):
+                                x[:, u * upe + j] *= sc[k, 2 * j] + 1j * sc[k, 2 * j + 1]
+                            k += 1
                     elif code == C_DIAGN:
                         nf = int(h0[1]) >> 16
                         f4, w = U[pay], U[pay + 1]
