@@ -115,6 +115,11 @@ int qj_collapse_state(qj_handle *h, void *state, int dtype, int nqubits, const i
                       int ntargets, int64_t result, int normalize);
 /* squared 2-norm of the state into a host double (synchronises). */
 int qj_norm2(qj_handle *h, const void *state, int dtype, int nqubits, double *out);
+/* max_i |state[i] - (ref_re + i ref_im)| into a host double (synchronises): the distance from a
+ * constant vector -- the closed form of the reference's own benchmark circuit QFT|0..0> =
+ * 2^(-n/2) everywhere (benchmarks/abstract.py:86-104) -- at sizes no host copy can check.   */
+int qj_max_deviation(qj_handle *h, const void *state, int dtype, int nqubits, double ref_re,
+                     double ref_im, double *out);
 /* replaces qibo Backend.calculate_probabilities (call sites gpu.py:751-768): probs is a
  * DEVICE array of 2^nmeas reals (float for C64, double for C128); bits[j] = index bit of the
  * j-th measured qubit, output index has j = 0 as its most significant bit.               */

@@ -40,6 +40,7 @@ SIGNATURES = {
     "qj_apply_multi_qubit_gate": (_I, [_P, _P, _I, _I, _P, _P, _I, _P, _I]),
     "qj_collapse_state": (_I, [_P, _P, _I, _I, _P, _I, _L, _I]),
     "qj_norm2": (_I, [_P, _P, _I, _I, _c.POINTER(_c.c_double)]),
+    "qj_max_deviation": (_I, [_P, _P, _I, _I, _c.c_double, _c.c_double, _c.POINTER(_c.c_double)]),
     "qj_calculate_probabilities": (_I, [_P, _P, _I, _I, _P, _I, _P]),
     "qj_measure_frequencies": (_I, [_P, _P, _P, _I, _L, _I, _L, _I]),
     "qj_sample_shots": (_I, [_P, _P, _I, _I, _P, _L, _P, _P]),

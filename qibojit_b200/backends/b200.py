@@ -294,8 +294,20 @@ class B200Backend(_QiboBackend):
         name = gate.__class__.__name__
         if name in ("Y", "CY"):
             return self._apply_ygate_density_matrix(gate, state, nqubits)
+        if name == "FanOut" or getattr(gate, "name", None) == "fanout":
+            # a loop of CNOTs (cpu.py:417-431), each its own inverse and real: U rho U^dagger in two halves
+            from .. import gates as G
+
+            for t in gate.target_qubits:
+                state = self._apply_gate_density_matrix(G.CNOT(gate.control_qubits[0], t), state, nqubits)
+            return state
         if inverse:
-            matrix = np.linalg.inv(np.asarray(self.matrix(gate)))
+            # cpu.py:464-468 inverts the gate's MATRIX (not the kernel-format buffer of U1 / fSim,
+            # which is a scalar / 5-vector) and applies it with the general kernels
+            from ..fusion import target_only_matrix
+
+            matrix = np.linalg.inv(np.asarray(target_only_matrix(gate, self.custom_matrices), dtype=np.complex128))
+            matrix = matrix.astype(self.dtype)
         else:
             matrix = self._as_custom_matrix(gate)
         qubits = self._create_qubits_tensor(gate, nqubits)
@@ -332,8 +344,10 @@ class B200Backend(_QiboBackend):
         return flat.reshape(shape)
 
     def matrix(self, gate):
-        """Full-space matrix of the gate's target part (used for channel inverses)."""
-        return self._as_custom_matrix(gate)
+        """2^t x 2^t matrix of the gate's target part (what the channel inverse inverts)."""
+        from ..fusion import target_only_matrix
+
+        return np.asarray(target_only_matrix(gate, self.custom_matrices))
 
     def matrix_fused(self, fgate):
         """Dense matrix of a ``FusedGate`` block (qibo ``Backend.matrix_fused``, called at
@@ -440,8 +454,26 @@ class B200Backend(_QiboBackend):
     # ------------------------------------------------------------------ measurement
     def collapse_state(self, state, qubits, shot, nqubits, normalize=True, density_matrix=False):
         if density_matrix:
-            raise NotImplementedError("density-matrix collapse is outside the state-vector path")
+            return self._collapse_density_matrix(state, qubits, shot, nqubits, normalize)
         return self._collapse_statevector(state, qubits, shot, nqubits, normalize)
+
+    def _collapse_density_matrix(self, state, qubits, shot, nqubits, normalize=True):
+        """P rho P / tr(P rho) with P the projector on outcome `shot` of `qubits` (qibo
+        ``collapse_density_matrix``): rho flattened to a 2n-qubit vector is collapsed on the row
+        AND the column copy of the measured qubits by the same zeroing kernel as a state vector
+        (ops.py:47-56 on 2n index bits); the normalisation is the trace, not a 2-norm."""
+        qubits = sorted(int(q) for q in qubits)
+        if hasattr(shot, "detach"):
+            shot = shot.detach().cpu().numpy()
+        shot = int(np.asarray(shot).flat[0]) if hasattr(shot, "shape") or hasattr(shot, "__len__") else int(shot)
+        shape = state.shape
+        flat = state.reshape(-1)
+        both = qubits + [q + nqubits for q in qubits]
+        flat = self._collapse_statevector(flat, both, (shot << len(qubits)) | shot, 2 * nqubits, normalize=False)
+        state = flat.reshape(shape)
+        if normalize:
+            state /= state.diagonal().sum()
+        return state
 
     def _collapse_statevector(self, state, qubits, shot, nqubits, normalize=True):
         # cpu.py:541-563
@@ -467,10 +499,31 @@ class B200Backend(_QiboBackend):
                                        ctypes.byref(out)))
         return float(np.sqrt(out.value))
 
+    def max_deviation(self, state, reference):
+        """max_i |state[i] - reference| for a scalar `reference`, on the device without a
+        state-sized temporary: the analytic check of QFT|0...0> = 2^(-n/2) at benchmark sizes."""
+        import ctypes
+
+        out = ctypes.c_double()
+        flat = state.reshape(-1)
+        nq = int(flat.numel()).bit_length() - 1
+        ref = complex(reference)
+        _capi.check(self._lib.qj_max_deviation(self._handle(), flat.data_ptr(), self._tag(flat), nq,
+                                               ref.real, ref.imag, ctypes.byref(out)))
+        return float(out.value)
+
     def calculate_probabilities(self, state, qubits, nqubits, density_matrix=False):
         torch = _torch()
         if density_matrix:
-            raise NotImplementedError("density-matrix probabilities are outside the state-vector path")
+            # qibo `calculate_probabilities_density_matrix`: |marginal of the diagonal| in `qubits` order
+            qubits = [int(q) for q in qubits]
+            diag = state.diagonal().reshape((2,) * nqubits)
+            rest = [q for q in range(nqubits) if q not in qubits]
+            if rest:
+                diag = diag.sum(dim=rest)
+            kept = sorted(qubits)
+            diag = diag.permute([kept.index(q) for q in qubits]) if len(qubits) > 1 else diag
+            return diag.abs().reshape(-1)
         qubits = list(qubits)
         bits = np.array([nqubits - q - 1 for q in qubits], dtype=np.int32)
         rdtype = torch.float64 if self._tag(state) == _capi.QJ_C128 else torch.float32

@@ -103,6 +103,44 @@ k_norm2(const Cx<T> *__restrict__ st, int64_t n, double *__restrict__ partials) 
     if (threadIdx.x == 0) partials[blockIdx.x] = s;
 }
 
+// max_i |st[i] - ref|: the distance of the state from a constant vector (the closed form of
+// QFT|0..0>, 2^(-n/2) everywhere) without a state-sized temporary; warp-shuffle + block tree
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+k_max_deviation(const Cx<T> *__restrict__ st, int64_t n, double rr, double ri, double *__restrict__ partials) {
+    const int64_t stride = int64_t(gridDim.x) * kThreads;
+    double acc = 0.0;
+    for (int64_t i = int64_t(blockIdx.x) * kThreads + threadIdx.x; i < n; i += stride) {
+        const Cx<T> a = st[i];
+        const double dr = double(a.re) - rr, di = double(a.im) - ri;
+        acc = fmax(acc, dr * dr + di * di);
+    }
+    __shared__ double warp_max[kThreads / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc = fmax(acc, __shfl_xor_sync(0xffffffffu, acc, o));
+    if ((threadIdx.x & 31) == 0) warp_max[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double m = 0.0;
+        for (int w = 0; w < kThreads / 32; w++) m = fmax(m, warp_max[w]);
+        partials[blockIdx.x] = m;
+    }
+}
+__global__ void __launch_bounds__(kThreads) k_finish_max(const double *partials, int n, double *out) {
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += kThreads) acc = fmax(acc, partials[i]);
+    __shared__ double warp_max[kThreads / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc = fmax(acc, __shfl_xor_sync(0xffffffffu, acc, o));
+    if ((threadIdx.x & 31) == 0) warp_max[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double m = 0.0;
+        for (int w = 0; w < kThreads / 32; w++) m = fmax(m, warp_max[w]);
+        out[0] = sqrt(m);
+    }
+}
+
 // ------------------------------------------------------------------ probabilities
 // (a) every qubit measured in natural order: |psi|^2 elementwise
 template <typename T>
@@ -553,6 +591,30 @@ extern "C" int qj_norm2(qj_handle *h, const void *state, int dtype, int nqubits,
     });
     if (rc) return rc;
     rc = launch_checked(h, [&] { k_finish_sum<<<1, kThreads, 0, h->stream>>>(h->scratch + 2, (int)grid, h->scratch); });
+    if (rc) return rc;
+    QJ_CUDA_OK(cudaMemcpyAsync(out, h->scratch, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    QJ_CUDA_OK(cudaStreamSynchronize(h->stream));
+    return QJ_OK;
+}
+
+extern "C" int qj_max_deviation(qj_handle *h, const void *state, int dtype, int nqubits, double ref_re,
+                                double ref_im, double *out) {
+    qj::DeviceGuard device_guard(h);
+    QJ_REQUIRE(h && state && out, "null argument");
+    QJ_REQUIRE(dtype == QJ_C64 || dtype == QJ_C128, "dtype must be QJ_C64 or QJ_C128");
+    QJ_REQUIRE(nqubits >= 0 && nqubits <= QJ_MAX_QUBITS, "nqubits out of range");
+    const int64_t n = int64_t(1) << nqubits;
+    const unsigned grid = persistent_grid(h, n, kThreads * 4);
+    int rc = launch_checked(h, [&] {
+        if (dtype == QJ_C128)
+            k_max_deviation<double><<<grid, kThreads, 0, h->stream>>>(reinterpret_cast<const Cx<double> *>(state), n,
+                                                                      ref_re, ref_im, h->scratch + 2);
+        else
+            k_max_deviation<float><<<grid, kThreads, 0, h->stream>>>(reinterpret_cast<const Cx<float> *>(state), n,
+                                                                     ref_re, ref_im, h->scratch + 2);
+    });
+    if (rc) return rc;
+    rc = launch_checked(h, [&] { k_finish_max<<<1, kThreads, 0, h->stream>>>(h->scratch + 2, (int)grid, h->scratch); });
     if (rc) return rc;
     QJ_CUDA_OK(cudaMemcpyAsync(out, h->scratch, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     QJ_CUDA_OK(cudaStreamSynchronize(h->stream));

@@ -109,6 +109,7 @@ struct PassGeom {
     int prefix_units;      // its leading part (header, rounds, outers, H and F entries): copied to shared memory
     int nH;                // per-tile phase factors (outer-only parts of the phase groups)
     int nF;                // fused diagonals with an outer part (2^J per-tile, per-element factors each)
+    int nFS;               // their slices in total (one table look-up per slice and tile)
 };
 
 // ---- program image (16-byte units) -------------------------------------------------------------
@@ -337,32 +338,51 @@ __device__ __forceinline__ void op_dense2(Cx<T> (&x)[Lay<T>::N], const ProgParam
 // re and im parts transform separately, 8 multiply-adds per amplitude instead of 16
 template <typename T, int A, int B>
 __device__ __forceinline__ void dense2r_group(Cx<T> (&x)[Lay<T>::N], const ProgParam &pp, int pay, int e0) {
-    Cx<T> s[4], y[4];
-#pragma unroll
-    for (int j = 0; j < 4; j++) s[j] = x[e0 | ((j & 1) << A) | ((j >> 1) << B)];
+    // "diagonal last": acc_i = sum_{j != i} g_ij s_j for every row first (all inputs still alive),
+    // then s_i = g_ii s_i + acc_i in place -- every result lands in the register its input came
+    // from, so the op loop needs no register shuffling at its back edge
+    constexpr int E0 = 0, E1 = 1 << A, E2 = 1 << B, E3 = (1 << A) | (1 << B);
+    const int idx[4] = {e0 | E0, e0 | E1, e0 | E2, e0 | E3};
     if constexpr (sizeof(T) == 4) {
+        u64 acc[4];
+        float gd[4];
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             float g[4];                                   // row i
             load_units<1>(pp, pay + i, g);
-            u64 acc = f2_mul(f2_splat(g[0]), f2_of(s[0]));
+            gd[i] = g[i];
+            bool first = true;
 #pragma unroll
-            for (int j = 1; j < 4; j++) acc = f2_fma(f2_splat(g[j]), f2_of(s[j]), acc);
-            f2_store(y[i], acc);
+            for (int j = 0; j < 4; j++) {
+                if (j == i) continue;
+                acc[i] = first ? f2_mul(f2_splat(g[j]), f2_of(x[idx[j]])) : f2_fma(f2_splat(g[j]), f2_of(x[idx[j]]), acc[i]);
+                first = false;
+            }
         }
+#pragma unroll
+        for (int i = 0; i < 4; i++) f2_store(x[idx[i]], f2_fma(f2_splat(gd[i]), f2_of(x[idx[i]]), acc[i]));
     } else {
+        T ar[4], ai[4], gd[4];
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             T g[4];
             load_units<2>(pp, pay + 2 * i, g);
-            T ar = g[0] * s[0].re, ai = g[0] * s[0].im;
+            gd[i] = g[i];
+            bool first = true;
 #pragma unroll
-            for (int j = 1; j < 4; j++) { ar = fma(g[j], s[j].re, ar); ai = fma(g[j], s[j].im, ai); }
-            y[i].re = ar; y[i].im = ai;
+            for (int j = 0; j < 4; j++) {
+                if (j == i) continue;
+                if (first) { ar[i] = g[j] * x[idx[j]].re; ai[i] = g[j] * x[idx[j]].im; }
+                else { ar[i] = fma(g[j], x[idx[j]].re, ar[i]); ai[i] = fma(g[j], x[idx[j]].im, ai[i]); }
+                first = false;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            x[idx[i]].re = fma(gd[i], x[idx[i]].re, ar[i]);
+            x[idx[i]].im = fma(gd[i], x[idx[i]].im, ai[i]);
         }
     }
-#pragma unroll
-    for (int i = 0; i < 4; i++) x[e0 | ((i & 1) << A) | ((i >> 1) << B)] = y[i];
 }
 
 template <typename T, int A, int B>
@@ -638,7 +658,8 @@ k_pass(Cx<T> *__restrict__ state, const __grid_constant__ PassGeom pg, const Cx<
     uint4 *const prog = tilev + nvec;
     uint4 *const s_H = prog + pg.prefix_units;                                      // one 16-byte slot per factor
     Cx<T> *const s_F = reinterpret_cast<Cx<T> *>(s_H + pg.nH);                      // N factors per fused diagonal
-    int64_t *const s_runoff = reinterpret_cast<int64_t *>(s_F + pg.nF * N);         // in vectors
+    uint4 *const s_FS = reinterpret_cast<uint4 *>(s_F + pg.nF * N);                 // one 16-byte slot per slice look-up
+    int64_t *const s_runoff = reinterpret_cast<int64_t *>(s_FS + pg.nFS);           // in vectors
     int32_t *const s_outer = reinterpret_cast<int32_t *>(s_runoff + (1 << pg.nh));
     uint4 *const gvec = reinterpret_cast<uint4 *>(state);
 
@@ -709,23 +730,35 @@ k_pass(Cx<T> *__restrict__ state, const __grid_constant__ PassGeom pg, const Cx<
             }
             *reinterpret_cast<Cx<T> *>(s_H + m) = acc;
         }
-        // per-tile, per-element factors of the fused diagonals
-        for (int m = tid; m < nF * N; m += nthr) {
-            const int f = m / N, e = m % N;
-            const uint4 dir = fents[f];
-            Cx<T> acc;
-            acc.re = T(1); acc.im = T(0);
-            for (uint32_t sl = 0; sl < dir.y; sl++) {
-                const uint4 u = fents[dir.x + sl];
-                if (!((u.x >> e) & 1u)) continue;
-                const int32_t v = outer_value(outers, int(u.z), base_amp);
-                if (v < 0) continue;
-                acc = cx_mul<T>(acc, ldg_cx(tables + u.y + v));
-            }
-            s_F[m] = acc;
+        // per-tile factors of the fused diagonals, stage 1: ONE table look-up per thread (all the
+        // slices of all fused diagonals in parallel: the latency of a single global load)
+        for (int m = tid; m < pg.nFS; m += nthr) {
+            const uint4 u = fents[nF + m];
+            const int32_t v = outer_value(outers, int(u.z), base_amp);
+            Cx<T> z;
+            z.re = T(1); z.im = T(0);
+            if (v >= 0) z = ldg_cx(tables + u.y + v);
+            *reinterpret_cast<Cx<T> *>(s_FS + m) = z;
         }
         cp_async_wait_all();
         __syncthreads();
+        // stage 2: per element, the product of the slices that cover it (two independent chains)
+        if (nF) {
+            for (int m = tid; m < nF * N; m += nthr) {
+                const int f = m / N, e = m % N;
+                const uint4 dir = fents[f];
+                Cx<T> acc0, acc1;
+                acc0.re = T(1); acc0.im = T(0); acc1 = acc0;
+                for (uint32_t sl = 0; sl < dir.y; sl += 2) {
+                    if ((fents[dir.x + sl].x >> e) & 1u)
+                        acc0 = cx_mul<T>(acc0, *reinterpret_cast<const Cx<T> *>(s_FS + (dir.x - nF + sl)));
+                    if (sl + 1 < dir.y && ((fents[dir.x + sl + 1].x >> e) & 1u))
+                        acc1 = cx_mul<T>(acc1, *reinterpret_cast<const Cx<T> *>(s_FS + (dir.x - nF + sl + 1)));
+                }
+                s_F[m] = cx_mul<T>(acc0, acc1);
+            }
+            __syncthreads();
+        }
 
         // ---- rounds
 #pragma unroll 1
@@ -1206,7 +1239,8 @@ static int program_build(qj_handle *h, int dtype, int nqubits, const qj_pass_des
             L.nops = launch_ops;
             L.geom.nH = int(h_units.size() / 4);
             L.geom.nF = int(f_dir.size());
-            L.smem = (size_t(1) << Tv) * 16 + size_t(off_ops) * 16 + (h_units.size() / 4) * 16 + f_dir.size() * 256 +
+            L.geom.nFS = int(f_slices.size());
+            L.smem = (size_t(1) << Tv) * 16 + size_t(off_ops) * 16 + (h_units.size() / 4) * 16 + f_dir.size() * 256 + f_slices.size() * 16 +
                      (size_t(8) << geo.nh) + (outer_units.size() / 2) * 4 + 16;
             prog->launches.push_back(L);
             blob_all.insert(blob_all.end(), img.begin(), img.end());

@@ -703,10 +703,18 @@ class Program:
     def fma_per_amplitude(self):
         """Real multiply-adds per amplitude the pass kernel executes for this program (the
         arithmetic side of the roofline): 4 for a real or axis-aligned one-target gate, 8 for a
-        complex one, 16 for a two-target gate (8 when its matrix is real), 4 per phase multiply; permutations and sign flips
-        cost none; controls scale by 2^-c."""
+        complex one, 16 for a two-target gate (8 when its matrix is real), 4 per phase multiply;
+        permutations and sign flips cost none; controls scale by 2^-c."""
+        return float(sum(self.fma_per_pass()))
+
+    def fma_per_pass(self):
+        """The same count, one entry per pass."""
+        return [self._fma_of(rounds) for _, rounds in self.passes]
+
+    @staticmethod
+    def _fma_of(rounds):
         total = 0.0
-        for _, rounds in self.passes:
+        if True:
             for _, ops in rounds:
                 for op in ops:
                     frac = 2.0 ** -len(op.controls)

@@ -23,7 +23,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def sass_lines(lib, kernel_substr, src_name):
     """[(opcode text, line)] for the first kernel whose mangled name contains `kernel_substr`."""
     tmp = tempfile.mkdtemp()
-    subprocess.run(["cuobjdump", "-xelf", "all", lib], cwd=tmp, capture_output=True)
+    subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, capture_output=True)
     out = []
     for f in sorted(os.listdir(tmp)):
         if not f.endswith(".cubin"):
