@@ -590,6 +590,11 @@ class B200Backend(_QiboBackend):
             return self.zero_state(nlocal, dtype=dtype)
         return torch.zeros(1 << nlocal, dtype=getattr(torch, str(dtype)), device=self.torch_device)
 
+    def shard_from(self, piece, dtype):
+        """This rank's piece of a caller-supplied state (host array or tensor on any device) as a
+        device shard of its own (the caller keeps its state, cpu.py:96-119 semantics of `cast`)."""
+        return self.cast(piece, dtype=str(dtype), copy=True).reshape(-1)
+
     def shard_reset(self, shard, nlocal, one_at_zero=False):
         if one_at_zero:
             _capi.check(self._lib.qj_initial_state(self._handle(), shard.data_ptr(), self._tag(shard), nlocal))

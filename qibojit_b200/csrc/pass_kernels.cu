@@ -89,6 +89,7 @@ enum {
     C_DENSE2R = 30,   // + pair index: REAL 4x4 (16 scalars): half the multiply-adds of the complex one
     C_DIAGF = 40,     // fused diagonal: per-thread, per-element factors G[tid][unit] (x per-tile factors)
     C_DIAGC = 41,     // constant diagonal: one complex constant per selected unit, in the payload
+    C_DIAGS = 42,     // slot-factorised diagonal: one factor per register slot and thread (x per-tile factor)
 };
 
 // element selection of a C_PHASE op (which of a thread's register amplitudes the phase multiplies)
@@ -573,6 +574,37 @@ __device__ __forceinline__ void op_diagf(Cx<T> (&x)[Lay<T>::N], const Cx<T> *__r
     }
 }
 
+// Slot-factorised diagonal: the phase groups waiting at one point of a round that each multiply
+// "the elements whose register bit s is 1" (the ladders of controlled phases behind the H gates of
+// a QFT round) in ONE op: the per-thread factors of all slots are 64 contiguous bytes per thread
+// (all loads issued together, tables a few KiB: L1 resident), the per-tile factors come from the
+// fused-diagonal machinery (entry 2^s of the op's per-element array), then x[e] *= Q_s for every
+// element with bit s set.  Same arithmetic as one phase group per slot, one dispatch and one
+// memory latency instead of J.
+template <typename T, bool HASF>
+__device__ __forceinline__ void op_diags(Cx<T> (&x)[Lay<T>::N], const Cx<T> *__restrict__ gp, uint32_t sm, bool has_g,
+                                         const Cx<T> *fp) {
+    constexpr int J = Lay<T>::J, N = Lay<T>::N;
+    Cx<T> q[J];
+#pragma unroll
+    for (int s = 0; s < J; s++) {
+        q[s].re = T(1); q[s].im = T(0);
+        if (has_g && ((sm >> s) & 1u)) q[s] = ldg_cx(gp + s);
+    }
+    if (HASF) {
+#pragma unroll
+        for (int s = 0; s < J; s++)
+            if ((sm >> s) & 1u) q[s] = cx_mul<T>(q[s], fp[1 << s]);
+    }
+#pragma unroll
+    for (int s = 0; s < J; s++) {
+        if (!((sm >> s) & 1u)) continue;
+#pragma unroll
+        for (int e = 0; e < N; e++)
+            if ((e >> s) & 1) cmul_inplace<T>(x[e], q[s].re, q[s].im);
+    }
+}
+
 // Constant diagonal: factors that depend on the register bits only (the phases between the H
 // gates of a QFT round, CZ / CU1 inside a register block): one complex constant per selected
 // 16-byte unit, read from the program image as uniform operands -- no memory traffic at all.
@@ -803,7 +835,7 @@ k_pass(Cx<T> *__restrict__ state, const __grid_constant__ PassGeom pg, const Cx<
                     const uint32_t code = h0.x & 0xffffu;
                     uint32_t emask = h0.w;
                     int oi = 0;
-                    if (code != C_PHASE && code != C_DIAGF && code != C_DIAGC && (h0.z != 0u || (h0.y & 0xffffu) != 0xffffu)) {   // predicated op
+                    if (code != C_PHASE && code < C_DIAGF && (h0.z != 0u || (h0.y & 0xffffu) != 0xffffu)) {   // predicated op
                         const uint32_t oslot = h0.y & 0xffffu, tmask = h0.z;
                         bool ok = (base & tmask) == tmask;
                         if (oslot != 0xffffu) {
@@ -951,6 +983,12 @@ k_pass(Cx<T> *__restrict__ state, const __grid_constant__ PassGeom pg, const Cx<
                             }
                         } break;
                         case C_DIAGC: op_diagc<T>(x, pp, pay, h0.w); break;
+                        case C_DIAGS: {   // h0.y = F index (0xffff: none) | has_g << 16, h0.w = slot mask, h1.x = G
+                            const uint32_t fidx = h0.y & 0xffffu;
+                            const Cx<T> *const gp = tables + h1.x + tid * (VS ? 8 : 4);
+                            if (fidx != 0xffffu) op_diags<T, true>(x, gp, h0.w, (h0.y >> 16) != 0u, s_F + fidx * N);
+                            else op_diags<T, false>(x, gp, h0.w, true, nullptr);
+                        } break;
                         default: {  // C_DIAGN: table index = outer part | fields of the base | element part
                             const int nf = int(h0.y >> 16);
                             const uint4 f = pp.u[pay], w = pp.u[pay + 1];
@@ -1159,6 +1197,8 @@ static int program_build(qj_handle *h, int dtype, int nqubits, const qj_pass_des
     // are at least this many of them (0: never); QJ_DIAGF_MIN overrides it for experiments
     int fuse_min = 2;
     if (const char *ev = getenv("QJ_DIAGF_MIN")) fuse_min = atoi(ev);
+    const bool generic_only = fuse_min >= 100;      // 100 + n: threshold n, never the slot-factorised form (tests)
+    if (generic_only) fuse_min -= 100;
 
     auto *prog = new qj_program();
     prog->dtype = dtype;
@@ -1437,6 +1477,68 @@ static int program_build(qj_handle *h, int dtype, int nqubits, const qj_pass_des
                             else if (ps.cls == 1 && any_f) fm.push_back(&ps);
                             else keep.push_back(ps);
                         }
+                        // every fused slice multiplies "the elements with register bit s set" for some
+                        // slot s: the slot-factorised form (J factors per thread instead of 2^J)
+                        auto slot_of = [&](uint32_t emask) -> int {
+                            for (int a = 0; a < J; a++) {
+                                uint32_t m = 0;
+                                for (int e = 0; e < N; e++) if ((e >> a) & 1) m |= 1u << e;
+                                if (m == emask) return a;
+                            }
+                            return -1;
+                        };
+                        bool by_slot = !generic_only;
+                        for (const PendingSlice *ps : gm) by_slot = by_slot && slot_of(ps->emask) >= 0;
+                        for (const PendingSlice *ps : fm) by_slot = by_slot && slot_of(ps->emask) >= 0;
+                        if (by_slot) {
+                            uint32_t smask = 0;
+                            for (const PendingSlice *ps : gm) smask |= 1u << slot_of(ps->emask);
+                            for (const PendingSlice *ps : fm) smask |= 1u << slot_of(ps->emask);
+                            uint32_t g_off = 0xffffffffu;
+                            if (!gm.empty()) {
+                                const int per = VS ? 8 : 4;     // factors per thread (64 bytes)
+                                std::vector<cd> G(size_t(nthr_round) * size_t(per), cd(1.0));   // [thread][slot]
+                                for (const PendingSlice *ps : gm) {
+                                    const int a = slot_of(ps->emask);
+                                    for (int t = 0; t < nthr_round; t++) {
+                                        const uint32_t base = thread_base(t);
+                                        if ((base & ps->tmask) != ps->tmask) continue;
+                                        uint32_t idx = 0;
+                                        for (int f = 0; f < ps->nf; f++) idx |= host_field(base, ps->fields[f]);
+                                        G[size_t(t) * size_t(per) + size_t(a)] *= ps->host[idx];
+                                    }
+                                }
+                                if (VS && ((enc.tables.size() / enc.esz) & 1)) enc.push_table(std::vector<cd>(1, cd(1.0)));
+                                g_off = enc.push_table(G);
+                            }
+                            uint32_t fidx = 0xffffu;
+                            if (!fm.empty()) {
+                                fidx = uint32_t(f_base) + uint32_t(r_Fdir.size());
+                                Unit d;
+                                memset(&d, 0, sizeof(d));
+                                d.w[0] = uint32_t(r_Fsl.size());
+                                d.w[1] = uint32_t(fm.size());
+                                r_Fdir.push_back(d);
+                                for (const PendingSlice *ps : fm) {
+                                    Unit u;
+                                    memset(&u, 0, sizeof(u));
+                                    u.w[0] = ps->emask; u.w[1] = ps->table; u.w[2] = uint32_t(ps->oslot);
+                                    r_Fsl.push_back(u);
+                                }
+                            }
+                            Unit h0, h1;
+                            memset(&h1, 0, sizeof(h1));
+                            h0.w[0] = uint32_t(C_DIAGS) | (2u << 16);
+                            h0.w[1] = fidx | ((gm.empty() ? 0u : 1u) << 16);
+                            h0.w[2] = 0;
+                            h0.w[3] = smask;
+                            h1.w[0] = g_off;
+                            r_ops.push_back(h0); r_ops.push_back(h1);
+                            r_nops++;
+                            pending = keep;
+                            gm.clear(); fm.clear();
+                        }
+                        if (!gm.empty() || !fm.empty()) {
                         uint32_t emu = 0;
                         for (const PendingSlice *ps : gm) emu |= ps->emask;
                         for (const PendingSlice *ps : fm) emu |= ps->emask;
@@ -1487,6 +1589,7 @@ static int program_build(qj_handle *h, int dtype, int nqubits, const qj_pass_des
                         r_ops.push_back(h0); r_ops.push_back(h1);
                         r_nops++;
                         pending = keep;
+                        }
                     }
                 }
                 std::vector<bool> done(pending.size(), false);
@@ -1830,7 +1933,8 @@ static int program_build(qj_handle *h, int dtype, int nqubits, const qj_pass_des
                             if (oslot != 0xffffu) r_ops[d].w[1] = nf | ((oslot - uint32_t(outer_base)) << 16);
                             d += (nf > 5) ? 3 : 2;
                         }
-                    } else if ((r_ops[i].w[0] & 0xffffu) == uint32_t(C_DIAGF)) {   // index of its per-tile factors
+                    } else if ((r_ops[i].w[0] & 0xffffu) == uint32_t(C_DIAGF) ||
+                               (r_ops[i].w[0] & 0xffffu) == uint32_t(C_DIAGS)) {   // index of its per-tile factors
                         const uint32_t fidx = r_ops[i].w[1] & 0xffffu;
                         if (fidx != 0xffffu) r_ops[i].w[1] = (r_ops[i].w[1] & 0xffff0000u) | (fidx - uint32_t(f_base));
                     } else {

@@ -163,7 +163,7 @@ class MultiExchange:
 class DistributedState:
     """A 2^nqubits state vector sharded over the ranks of `comm`."""
 
-    def __init__(self, backend, nqubits, comm=None, dtype=None, swap_chunk_bytes=1 << 29):
+    def __init__(self, backend, nqubits, comm=None, dtype=None, swap_chunk_bytes=1 << 29, initial_state=None):
         self.backend = backend
         self.comm = comm if comm is not None else Comm()
         self.nqubits = int(nqubits)
@@ -179,7 +179,18 @@ class DistributedState:
         self.stats = {"exchanges": 0, "exchange_bytes": 0, "local_gates": 0, "local_segments": 0,
                       "skipped": 0, "relabelled_swaps": 0}
         self._fresh = True   # still |0...0>: the qubit map may be chosen freely
-        self.shard = backend.shard_zeros(self.nlocal, self.dtype, one_at_zero=(self.rank == 0))
+        self.relabel_swaps = True
+        if initial_state is None:
+            self.shard = backend.shard_zeros(self.nlocal, self.dtype, one_at_zero=(self.rank == 0))
+        else:
+            # the reference's piece layout for global qubits [0..g-1] (gpu.py:1440-1442): rank r
+            # takes the contiguous slice [r * 2^nlocal, (r+1) * 2^nlocal) of the full vector
+            size = 1 << self.nlocal
+            flat = initial_state.reshape(-1)
+            if int(flat.shape[0]) != (1 << self.nqubits):
+                raise TypeError(f"initial state has {int(flat.shape[0])} amplitudes, expected 2^{self.nqubits}")
+            self.shard = backend.shard_from(flat[self.rank * size:(self.rank + 1) * size], self.dtype)
+            self._fresh = False
 
     # ------------------------------------------------------------------ helpers
     def is_local(self, q):
@@ -265,7 +276,7 @@ class DistributedState:
         controls = list(gate.control_qubits)
         op = GATE_OPS.get(name)
 
-        if op == "apply_swap" and not controls:
+        if op == "apply_swap" and not controls and self.relabel_swaps:
             # relabel: the data does not move, the two logical qubits trade index bits
             a, c = targets
             self.bit_of[a], self.bit_of[c] = self.bit_of[c], self.bit_of[a]
@@ -371,7 +382,7 @@ class DistributedState:
                 gates.extend(G.CNOT(g.control_qubits[0], t) for t in g.target_qubits)
             else:
                 gates.append(g)
-        needs = [self._needs_local(g, self.backend.custom_matrices) for g in gates]
+        needs = [self._needs_local(g, self.backend.custom_matrices, self.relabel_swaps) for g in gates]
         if free_initial_map is None:
             free_initial_map = self._fresh and reorder
         if free_initial_map and self.nglobal:
@@ -545,13 +556,13 @@ class DistributedState:
 
     # ------------------------------------------------------------------ circuits
     @staticmethod
-    def _needs_local(gate, custom_matrices):
+    def _needs_local(gate, custom_matrices, relabel_swaps=True):
         """Qubits of `gate` that must be local for it to run (non-diagonal targets)."""
         name = gate.__class__.__name__
         op = GATE_OPS.get(name)
         if op in _SYMMETRIC_PHASE_OPS or getattr(gate, "diagonal", False):
             return []
-        if op == "apply_swap" and not gate.control_qubits:
+        if op == "apply_swap" and not gate.control_qubits and relabel_swaps:
             return []
         if name == "FusedGate":
             from . import fusion
@@ -592,6 +603,117 @@ class DistributedState:
         t = b.engine.tensor([val], dtype=b.engine.float64, device=self.shard.device)
         return float(self.comm.all_reduce_sum(t)[0])
 
+    # ------------------------------------------------------------------ layout
+    def normalize_layout(self):
+        """Bring the shards back to the reference's piece layout -- logical qubit q on index bit
+        n-1-q, qubits [0..g-1] global (gpu.py:1440-1442, 1454-1456) -- ON THE DEVICES: the
+        relabelled SWAPs and the scheduler's exchanges left a permuted qubit map that only
+        `to_numpy_full` undid (on the host).  The permutation is executed as data movement: at most
+        two multi-qubit exchanges put the right qubits on the rank bits, then one local segment of
+        SWAP gates (compiled into a few multi-gate passes) orders the shard.  Semantics of
+        ops.transpose_state (ops.py:112-124) followed by to_pieces."""
+        n, nl = self.nqubits, self.nlocal
+        want = lambda bit: n - 1 - bit                      # logical qubit that belongs on `bit`
+        steps = Plan()
+        steps.initial_map = list(self.bit_of)
+        for _ in range(4 * max(1, self.nglobal)):
+            wrong = [p for p in range(nl, n) if self.bit_of[want(p)] != p]
+            if not wrong:
+                break
+            pairs, used = [], set()
+            for p in wrong:
+                q = want(p)
+                if self.is_local(q) and q not in used and not (self.dtype == "complex64" and self.bit_of[q] == 0):
+                    pairs.append((self.qubit_at(p), q))
+                    used.add(q)
+            if not pairs:
+                # the wanted qubits sit on other rank bits (or on index bit 0 of a complex64
+                # shard): park one occupant on a local bit that nobody claims
+                p = wrong[0]
+                claimed = {want(b) for b in range(nl, n)}
+                victims = [v for v in range(n) if self.is_local(v) and v not in claimed
+                           and not (self.dtype == "complex64" and self.bit_of[v] == 0)]
+                if not victims:     # tiny shards: move the complex64 bit-0 qubit up first
+                    low = self.qubit_at(0)
+                    other = next(v for v in range(n) if self.is_local(v) and v != low)
+                    self._emit_move(steps, low, other)
+                    continue
+                pairs = [(self.qubit_at(p), victims[0])]
+            self._plan_multi_exchange(steps, pairs)
+        else:
+            raise RuntimeError("normalize_layout did not converge")
+        for p in range(nl):                                  # cycle decomposition on the local bits
+            while self.bit_of[want(p)] != p:
+                self._emit_move(steps, self.qubit_at(p), want(p))
+        steps.final_map = list(self.bit_of)
+        assert self.bit_of == [n - 1 - q for q in range(n)]
+        return self.run(steps)
+
+    def _emit_move(self, plan, qa, qb):
+        """Exchange the index bits of two LOCAL logical qubits by moving data (a physical SWAP
+        gate plus the relabelling that compensates it: the logical state is unchanged)."""
+        pa, pb = self._pseudo(self.bit_of[qa]), self._pseudo(self.bit_of[qb])
+        swap = np.array([[1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]], dtype=np.complex128)
+        self._emit(plan, LocalGate("apply_swap", [pa, pb], [], None, swap))
+        self.bit_of[qa], self.bit_of[qb] = self.bit_of[qb], self.bit_of[qa]
+
+    def to_pieces(self):
+        """This rank's piece in the reference's layout (gpu.py:1437-1449), on the device."""
+        self.normalize_layout()
+        return self.shard
+
+    def to_tensor(self):
+        """The full state vector in logical order on every rank's device (gpu.py:1451-1465 builds
+        it on the host): normalise the layout, then all-gather the pieces."""
+        self.normalize_layout()
+        pieces = self.comm.all_gather(self.shard)
+        return pieces[0] if len(pieces) == 1 else self.backend.engine.cat(pieces)
+
+    # ------------------------------------------------------------------ measurement
+    def collapse(self, qubits, shot, normalize=True):
+        """Projective collapse of logical `qubits` onto outcome `shot` (most significant bit =
+        lowest-numbered qubit, cpu.py:541-563 / ops.py:47-79) on the sharded state: local measured
+        qubits are zeroed by the collapse kernel, ranks whose global bits disagree with the
+        outcome zero their shard, the norm is all-reduced and every rank rescales."""
+        b = self.backend
+        qubits = sorted(int(q) for q in qubits)
+        k = len(qubits)
+        outcome = {q: (int(shot) >> (k - 1 - i)) & 1 for i, q in enumerate(qubits)}
+        alive = all(self.is_local(q) or self.rank_bit(q) == outcome[q] for q in qubits)
+        if not alive:
+            self.shard = b.shard_reset(self.shard, self.nlocal, one_at_zero=False)
+        else:
+            local = sorted((self._pseudo(self.bit_of[q]), outcome[q]) for q in qubits if self.is_local(q))
+            if local:
+                lshot = 0
+                for _, bit in local:
+                    lshot = (lshot << 1) | bit
+                self.shard = b.collapse_state(self.shard, [p for p, _ in local], lshot, self.nlocal, normalize=False)
+        self._fresh = False
+        if normalize:
+            norm = float(np.sqrt(self.norm2()))
+            self.shard = b.shard_scale(self.shard, self.nlocal, 1.0 / norm)
+        return self
+
+    def full_probabilities(self):
+        """|amplitude|^2 of the whole register in logical order, on every rank (the input of the
+        reference's samplers).  Needs 2^n reals per device: registers up to ~34 qubits."""
+        self.normalize_layout()
+        b = self.backend
+        local = b.calculate_probabilities(self.shard, list(range(self.nlocal)), self.nlocal)
+        pieces = self.comm.all_gather(local)
+        return pieces[0] if len(pieces) == 1 else b.engine.cat(pieces)
+
+    def sample_frequencies(self, nshots):
+        """`Backend.sample_frequencies` (cpu.py:383-394) on the sharded state: the same sampler --
+        the reference's Metropolis chains above the shot threshold (ops.py:86-108), bit-exact under
+        a fixed seed -- runs on the gathered probability vector; every rank returns the same
+        Counter (same seed stream)."""
+        return self.backend.sample_frequencies(self.full_probabilities(), nshots)
+
+    def sample_shots(self, nshots):
+        return self.backend.sample_shots(self.full_probabilities(), nshots)
+
     def to_numpy_full(self):
         """Gather every shard and undo the qubit relabelling (small registers / tests only)."""
         pieces = self.comm.all_gather(self.shard)
@@ -604,15 +726,26 @@ class DistributedState:
 
 
 def execute_distributed_circuit(backend, circuit, initial_state=None, nshots=None, comm=None):
-    if initial_state is not None:
-        raise TypeError("distributed execution starts from |0...0>; initial states are not supported")
-    state = DistributedState(backend, circuit.nqubits, comm=comm)
+    """`CupyBackend.execute_distributed_circuit` (gpu.py:646-739): `initial_state` may be None
+    (|0...0>), a full state vector (numpy array or tensor: every rank takes its piece,
+    gpu.py:669-676) or a DistributedState; anything else is a TypeError (gpu.py:677-682).  With
+    `nshots` the register is sampled (`sample_frequencies`) and (state, frequencies) is returned."""
+    if isinstance(initial_state, DistributedState):
+        state = initial_state
+    elif initial_state is None:
+        state = DistributedState(backend, circuit.nqubits, comm=comm)
+    elif hasattr(initial_state, "shape") and hasattr(initial_state, "reshape"):
+        state = DistributedState(backend, circuit.nqubits, comm=comm, initial_state=initial_state)
+    else:
+        raise TypeError(f"Initial state type {type(initial_state)} is not supported by distributed circuits.")
     fingerprint = (len(circuit.queue), getattr(backend, "circuit_fingerprint", len)(circuit.queue))
-    key = ("dist", state.rank, state.comm.world, backend.dtype)
+    key = ("dist", state.rank, state.comm.world, backend.dtype, tuple(state.bit_of), state._fresh)
     cache = circuit.__dict__.setdefault("_qj_programs", {})
     entry = cache.get(key)
     if entry is None or entry[0] != fingerprint:     # (an outdated plan is dropped with its programs)
         entry = cache[key] = (fingerprint, state.plan(circuit.queue))
     steps = entry[1]
     state.run(steps)
+    if nshots:
+        return state, state.sample_frequencies(int(nshots))
     return state

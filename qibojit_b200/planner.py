@@ -56,7 +56,7 @@ DIAGONAL_GATES = frozenset({
 DEFAULT_TILE_BITS = {"complex128": 11, "complex64": 13}
 # contiguous run of a tile in global memory: 256 bytes (whole sectors; measured as fast as 512-byte
 # runs and it leaves one more tile bit for arbitrary high qubits: fewer passes)
-DEFAULT_RUN_BITS = {"complex128": 4, "complex64": 5}
+DEFAULT_RUN_BITS = {"complex128": 3, "complex64": 5}
 MAX_TILE_BITS = {"complex128": 12, "complex64": 13}   # 64 KiB tiles, two resident CTAs per SM
 REG_BITS = {"complex128": 4, "complex64": 5}          # register bits per round (complex64: bit 0 + 4)
 MAX_HI_BITS = 8

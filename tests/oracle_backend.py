@@ -53,7 +53,27 @@ class OracleBackend:
     def calculate_norm(self, state):
         return float(np.linalg.norm(state.numpy()))
 
+    def collapse_state(self, state, qubits, shot, nqubits, normalize=True, density_matrix=False):
+        R.collapse(O, state.numpy(), sorted(qubits), shot, nqubits, normalize)
+        return state
+
+    def sample_frequencies(self, probabilities, nshots):
+        """Same seed draw and sampler as cpu.py:383-394 above the Metropolis threshold."""
+        from collections import Counter
+
+        seed = int(np.random.randint(0, int(1e8), size=1, dtype=np.int64)[0])
+        probs = probabilities.numpy()
+        nq = int(probs.size).bit_length() - 1
+        freqs = np.zeros(probs.size, dtype=np.int64)
+        O.measure_frequencies(freqs, probs, int(nshots), nq, seed, 4)
+        nz = np.nonzero(freqs)[0]
+        return Counter(dict(zip(nz.tolist(), freqs[nz].tolist())))
+
     # --- shard primitives
+    def shard_from(self, piece, dtype):
+        arr = piece.numpy() if hasattr(piece, "numpy") else np.asarray(piece)
+        return torch.from_numpy(np.array(arr, dtype=dtype, copy=True).reshape(-1))
+
     def shard_zeros(self, nlocal, dtype, one_at_zero=False):
         if one_at_zero:
             return self.zero_state(nlocal, dtype)

@@ -16,7 +16,7 @@ import numpy as np
 from qibojit_b200 import _capi, planner
 
 C_GROUP1C, C_GROUP1R, C_GROUP1X, C_PERM1, C_DENSE2, C_PERM2, C_PHASE, C_DIAGN = 0, 1, 2, 3, 8, 18, 28, 29
-C_DENSE2R, C_DIAGF, C_DIAGC = 30, 40, 41
+C_DENSE2R, C_DIAGF, C_DIAGC, C_DIAGS = 30, 40, 41, 42
 SEL_ALL, SEL_SLOT, SEL_PAIR, SEL_MASK = 0, 1, 6, 16
 PAIRS = [(0, 1), (0, 2), (1, 2), (0, 3), (1, 3), (2, 3), (0, 4), (1, 4), (2, 4), (3, 4)]
 
@@ -199,7 +199,7 @@ def run_image(image, state):
                     op += units
                     emask = np.full(nthr, int(h0[3]), dtype=np.int64)
                     oi = 0
-                    if code not in (C_PHASE, C_DIAGF, C_DIAGC) and (int(h0[2]) != 0 or (int(h0[1]) & 0xffff) != 0xffff):
+                    if code not in (C_PHASE, C_DIAGF, C_DIAGC, C_DIAGS) and (int(h0[2]) != 0 or (int(h0[1]) & 0xffff) != 0xffff):
                         oslot, tmask = int(h0[1]) & 0xffff, int(h0[2])
                         ok = (base & tmask) == tmask
                         if oslot != 0xffff:
@@ -319,6 +319,19 @@ def run_image(image, state):
                                 if fidx != 0xffff:
                                     z = z * s_F[fidx, ee]
                                 x[:, ee] *= z
+                        assert units == 2
+                    elif code == C_DIAGS:
+                        fidx, has_g, smask = int(h0[1]) & 0xffff, int(h0[1]) >> 16, int(h0[3])
+                        per = 8 if VS else 4                        # factors per thread in the table
+                        for a in range(J):
+                            if not (smask >> a) & 1:
+                                continue
+                            z = np.ones(nthr, dtype=np.complex128)
+                            if has_g:
+                                z = image.tables[int(h1[0]) + tid * per + a]
+                            if fidx != 0xffff:
+                                z = z * s_F[fidx, 1 << a]
+                            x[:, ((e >> a) & 1).astype(bool)] *= z[:, None]
                         assert units == 2
                     elif code == C_DIAGC:
                         um = int(h0[3])
