@@ -1,5 +1,12 @@
-"""N > 1 leg of bench.py: the same workload circuit, state sharded over the ranks
-(strong scaling: the circuit and its 2^n amplitudes are fixed, each rank holds 2^n / N)."""
+"""N > 1 leg of bench.py: the workload circuit with its state sharded over the ranks (strong
+scaling: the circuit and its 2^n amplitudes are fixed, each rank holds 2^n / N).
+
+Primary workload: the supremacy-style circuit on 34 qubits in complex64 (137 GB: it fits one GPU,
+so the N = 1 point of the series exists -- `secondary.supremacy` of the `--gpus 1` line).  Secondary
+records of the same JSON line: QFT-33 complex128 sharded (BASELINE configs[2] on N GPUs) and, on 8
+ranks, supremacy-36 complex64 (configs[3], 550 GB of state).  Every record carries its parity check:
+QFT against the closed form on every shard, supremacy against the committed 4-qubit marginal of the
+1-GPU run (tests/golden/marginals.json)."""
 
 import json
 import time
@@ -47,15 +54,51 @@ class TimedBackend:
                            peer, is_upper, comm, chunk_bytes)
 
 
-def run_distributed(args, backend, nqubits, dtype, fuse, world, rank):
+def _check_parity(state, workload, nqubits, dtype, dist):
+    """Parity of the sharded final state at benchmark size; raises on a mismatch above tolerance."""
+    import torch
+
+    from bench import MARGINAL_QUBITS, TOL, marginal_fixture
+
+    b = state.backend
+    tol = TOL[dtype]
+    out = {"tolerance": tol}
+    if workload == "qft":
+        err = torch.tensor([b.max_deviation(state.shard, 2.0 ** (-nqubits / 2))], device="cuda", dtype=torch.float64)
+        dist.all_reduce(err, op=dist.ReduceOp.MAX)
+        out.update(check="max |amp - 2^(-n/2)| over every shard (closed form of QFT|0..0>), on the devices",
+                   max_abs_err=float(err[0]))
+        if not out["max_abs_err"] <= tol:
+            raise AssertionError(f"parity: sharded qft-{nqubits} deviates by {out['max_abs_err']:.3e} > {tol}")
+        return out
+    marg = state.probabilities(MARGINAL_QUBITS).double().cpu().numpy()
+    out["marginal_sum"] = float(marg.sum())
+    fx = marginal_fixture(workload, nqubits, dtype)
+    if fx is None:
+        out.update(check="4-qubit marginal sums to 1 (no reference marginal at this size)", pinned=False)
+        if abs(out["marginal_sum"] - 1.0) > (1e-9 if dtype == "complex128" else 1e-4):
+            raise AssertionError(f"parity: marginal of sharded {workload}-{nqubits} sums to {out['marginal_sum']}")
+        return out
+    ref, src = fx
+    err = float(np.abs(marg - ref).max())
+    out.update(check=f"4-qubit marginal (qubits {MARGINAL_QUBITS}) vs {src}", max_abs_err=err, pinned=True)
+    if not err <= tol:
+        raise AssertionError(f"parity: marginal of sharded {workload}-{nqubits} {dtype} differs by {err:.3e} > {tol}")
+    return out
+
+
+def time_sharded(backend, workload, nqubits, dtype, steps, warmup, world, rank):
+    """Plan once, then time `steps` executions of the sharded circuit (device events, max over
+    ranks).  Returns the record (same fields as bench.time_program) on every rank."""
     import torch
     import torch.distributed as dist
 
     from bench import ClockSampler, build_circuit, measured_peak_gbs
-    from qibojit_b200.distributed import Comm, DistributedState
+    from qibojit_b200.distributed import Comm, DistributedState, LocalSegment
 
     amp = 16 if dtype == "complex128" else 8
-    circuit = build_circuit(args.workload, nqubits)
+    backend.set_dtype(dtype)
+    circuit = build_circuit(workload, nqubits)
     ngates = circuit.ngates
     comm = Comm()
     nlocal = nqubits - (world.bit_length() - 1)
@@ -64,15 +107,14 @@ def run_distributed(args, backend, nqubits, dtype, fuse, world, rank):
     # plan once: exchanges by look-ahead, this rank's local gates between them compiled into
     # multi-gate pass programs on first use (the warm-up steps)
     t0 = time.perf_counter()
-    steps = state.plan(circuit.queue)
+    steps_plan = state.plan(circuit.queue)
     plan_ms = 1e3 * (time.perf_counter() - t0)
 
     def step():
-        # re-prepare |0..0> in place and run the circuit
-        state.reset()
-        state.run(steps)
+        state.reset()          # re-prepare |0..0> in place
+        state.run(steps_plan)
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step()
     torch.cuda.synchronize()
     dist.barrier()
@@ -85,7 +127,7 @@ def run_distributed(args, backend, nqubits, dtype, fuse, world, rank):
         torch.cuda.synchronize()
         dist.barrier()
         e0.record()
-        for _ in range(args.steps):
+        for _ in range(steps):
             step()
         e1.record()
         torch.cuda.synchronize()
@@ -93,10 +135,8 @@ def run_distributed(args, backend, nqubits, dtype, fuse, world, rank):
     tb.enabled = False
     ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    total_ms = float(ms[0])
+    ms_per_step = float(ms[0]) / steps
     launches = backend.launch_count() - launches0
-    ms_per_step = total_ms / args.steps
-    value = ngates / (ms_per_step * 1e-3)
 
     per_kind = {}
     for kind, alg, a, b in tb.records:
@@ -106,66 +146,133 @@ def run_distributed(args, backend, nqubits, dtype, fuse, world, rank):
         d["n"] += 1
     local = {k: v for k, v in per_kind.items() if k != "exchange"}
     dom = max(local, key=lambda k: local[k]["ms"])
-    names = {"pass": "k_pass (multi-gate tile pass, 2*shard bytes per launch)"}
     peak, peak_src = measured_peak_gbs()
     achieved = local[dom]["bytes"] / (local[dom]["ms"] * 1e-3) / 1e9
-    breakdown = {k: {"launches_per_step": v["n"] / args.steps, "avg_ms": v["ms"] / v["n"],
-                     "gbs": v["bytes"] / (v["ms"] * 1e-3) / 1e9} for k, v in per_kind.items()}
-
-    # end to end: gate objects in, marginal probabilities out.  The timed state is released first
-    # (a 34-qubit complex128 shard is 128 GiB of the 180 GB)
+    breakdown = {k: {"launches_per_step": v["n"] / steps, "avg_ms": v["ms"] / v["n"],
+                     "ms_per_step": v["ms"] / steps, "gbs": v["bytes"] / (v["ms"] * 1e-3) / 1e9}
+                 for k, v in per_kind.items()}
     stats = dict(state.stats)
+    parity = _check_parity(state, workload, nqubits, dtype, dist)
+    h2d = sum(st.compiled.upload_bytes for st in steps_plan if isinstance(st, LocalSegment) and st.compiled is not None)
+    record = {
+        "workload": f"{workload}-{nqubits}-{dtype}", "circuit_gates": ngates, "n_gpus": world,
+        "ms_per_step": ms_per_step, "value": ngates / (ms_per_step * 1e-3),
+        "plan_ms": plan_ms, "local_segments": sum(isinstance(st, LocalSegment) for st in steps_plan),
+        "shard_bytes": amp << nlocal, "exchanges_per_step": stats["exchanges"] / steps,
+        "exchange_bytes_per_rank_per_step": stats["exchange_bytes"] / steps,
+        "exchange_transport": "peer memory (CUDA IPC over NVLink, in-place swap kernel)"
+                              if getattr(backend, "_peer_cache", None) else "NCCL send/recv through staging buffers",
+        "gpu_launches": int(launches), "program_upload_bytes": int(h2d),
+        "roofline": {"bound": "hbm", "kernel": "k_pass (multi-gate tile pass, 2*shard bytes per launch)" if dom == "pass" else dom,
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "peak_source": peak_src, "per_kernel": breakdown,
+                     "exchange_note": "exchange GB/s = bytes sent per rank / time; NVLink reference 770 GB/s per direction"},
+        "parity": parity, "clocks": clocks.summary(),
+    }
+    torch.cuda.synchronize()
+    dist.barrier()
+    backend.release_peer_mappings()        # before any rank frees its shard
+    dist.barrier()
     state.shard = None
+    del state
     torch.cuda.empty_cache()
-    e2e_times = []
-    host = None
-    for i in range(3):
+    return record, circuit
+
+
+def time_sharded_e2e(backend, circuit, nqubits, dtype, reps):
+    """End to end: gate objects in, marginal probabilities out; plans, compiles and uploads inside
+    the timed region."""
+    import torch
+    import torch.distributed as dist
+
+    from bench import MARGINAL_QUBITS
+    from qibojit_b200.distributed import Comm, DistributedState
+
+    comm = Comm()
+    times, host = [], None
+    for i in range(1 + reps):
         torch.cuda.synchronize()
         dist.barrier()
         t0 = time.perf_counter()
         ds = DistributedState(backend, nqubits, comm=comm, dtype=dtype)
-        ds.execute(circuit.queue)   # plans, compiles and uploads inside the timed region
-        host = ds.probabilities([0, 1, 2, 3]).cpu().numpy()
+        ds.execute(circuit.queue)
+        host = ds.probabilities(MARGINAL_QUBITS).cpu().numpy()
         torch.cuda.synchronize()
         dist.barrier()
         if i:
-            e2e_times.append(time.perf_counter() - t0)
+            times.append(time.perf_counter() - t0)
         ds.shard = None     # back to torch's caching allocator: the next step reuses the block
         del ds
-    t = torch.tensor([float(np.mean(e2e_times))], device="cuda", dtype=torch.float64)
+    dist.barrier()
+    backend.release_peer_mappings()
+    dist.barrier()
+    t = torch.tensor([float(np.mean(times))], device="cuda", dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = ngates / float(t[0])
-    from qibojit_b200.distributed import LocalSegment
-
-    h2d = sum(st.compiled.upload_bytes for st in steps if isinstance(st, LocalSegment) and st.compiled is not None)
     assert abs(host.sum() - 1.0) < (1e-6 if dtype == "complex128" else 1e-3), host.sum()
+    return {"value": circuit.ngates / float(t[0]), "unit": "gates/s", "ms_per_step": 1e3 * float(t[0]),
+            "d2h_bytes_per_step": int(host.nbytes),
+            "includes": "planning, program encode + upload on every rank, state preparation, all passes and "
+                        "exchanges, marginal all-reduce + read-back (the final state stays sharded on the devices)"}
+
+
+def run_distributed(args, backend, world, rank):
+    import torch
+    import torch.distributed as dist
+
+    from bench import DEFAULTS
+
+    workload = args.workload or "supremacy"
+    cfg = DEFAULTS[workload]
+    nqubits = args.nqubits or cfg["nqubits"]
+    dtype = args.dtype or cfg["dtype"]
+
+    primary, circuit = time_sharded(backend, workload, nqubits, dtype, args.steps, args.warmup, world, rank)
+    e2e = time_sharded_e2e(backend, circuit, nqubits, dtype, min(args.steps, 2))
+    e2e["h2d_bytes_per_step"] = primary["program_upload_bytes"]
+    torch.cuda.empty_cache()
+
+    secondary = {}
+    if not args.no_secondary and not args.workload:
+        extra = [("qft", 33, "complex128")]
+        if world == 8:
+            extra.append(("supremacy", 36, "complex64"))
+        for name, n, dt in extra:
+            try:
+                rec, _ = time_sharded(backend, name, n, dt, min(args.steps, 3), 3, world, rank)
+            except AssertionError:
+                raise
+            except Exception as exc:
+                rec = {"error": f"{type(exc).__name__}: {exc}"}
+            secondary[f"{name}-{n}"] = rec
+            torch.cuda.empty_cache()
 
     if rank == 0:
         line = {
-            "metric": "gates_per_second", "value": value, "unit": "gates/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "metric": "gates_per_second", "value": primary["value"], "unit": "gates/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": primary["ms_per_step"],
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64" if dtype == "complex128" else "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}-{nqubits}-{dtype}", "circuit_gates": ngates,
-                       "execution": "per-rank multi-gate tile passes between exchanges", "plan_ms": plan_ms,
-                       "local_segments": sum(isinstance(st, LocalSegment) for st in steps),
-                       "shard_bytes": amp << nlocal,
-                       "exchanges_per_step": stats["exchanges"] / args.steps,
-                       "exchange_bytes_per_rank_per_step": stats["exchange_bytes"] / args.steps,
-                       "parallelism": f"state sharded over {world} ranks on the top {world.bit_length() - 1} qubits, "
-                                      "NCCL qubit exchanges (pairwise half-shard swap for one qubit, "
+            "config": {"workload": primary["workload"], "circuit_gates": primary["circuit_gates"],
+                       "execution": "per-rank multi-gate tile passes between exchanges", "plan_ms": primary["plan_ms"],
+                       "local_segments": primary["local_segments"], "shard_bytes": primary["shard_bytes"],
+                       "exchanges_per_step": primary["exchanges_per_step"],
+                       "exchange_bytes_per_rank_per_step": primary["exchange_bytes_per_rank_per_step"],
+                       "exchange_transport": primary["exchange_transport"],
+                       "parallelism": f"state sharded over {world} ranks on the top {world.bit_length() - 1} qubits; "
+                                      "qubit exchanges over NVLink (pairwise half-shard swap for one qubit, "
                                       "all-to-all of (2^k-1)/2^k of a shard for k qubits)",
+                       "strong_scaling_n1": "the N = 1 point of this workload is `secondary.supremacy` of the "
+                                            "`--gpus 1` line (its primary workload is QFT-33 complex128)",
                        "l2_policy": "shards are far larger than the 126 MB L2; no flush needed",
                        "timing": "CUDA events on the launch stream, max over ranks"},
-            "roofline": {"bound": "hbm", "kernel": names.get(dom, dom), "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                         "per_kernel": breakdown,
-                         "exchange_note": "exchange GB/s = bytes sent per rank / time; NVLink reference 770 GB/s per direction"},
-            "e2e": {"value": e2e_value, "unit": "gates/s", "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(host.nbytes)},
-            "gpu_launches": int(launches),
-            "clocks": clocks.summary(),
+            "roofline": primary["roofline"],
+            "parity": primary["parity"],
+            "e2e": e2e,
+            "gpu_launches": primary["gpu_launches"],
+            "clocks": primary["clocks"],
         }
+        if secondary:
+            line["secondary"] = secondary
         print(json.dumps(line))
     dist.barrier()
     dist.destroy_process_group()

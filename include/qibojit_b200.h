@@ -146,6 +146,18 @@ int qj_sample_shots(qj_handle *h, const void *probs, int real_dtype, int nqubits
  * together the two calls perform piece0[i + 2^m] <-> piece1[i] for all i with bit m clear. */
 int qj_swap_pieces_peer(qj_handle *h, void *local, void *peer, int dtype, int nlocal, int m,
                         int is_upper);
+/* The same exchange for SEVERAL qubits at once over peer memory (the all-to-all of a multi-qubit
+ * global<->local swap, one call per peer): this rank's sub-block whose index bits `bits`
+ * (ascending) spell `local_value` trades places with the peer's sub-block that spells
+ * `peer_value`.  The two ranks of a pair each call it with their own `part` of `nparts` (0 / 1 of
+ * 2): together they move every amplitude once.  No staging buffer, no pack / unpack pass.      */
+int qj_swap_bits_peer(qj_handle *h, void *local, void *peer, int dtype, int nlocal, const int32_t *bits,
+                      int nbits, int local_value, int peer_value, int part, int nparts);
+/* CUDA IPC plumbing of the peer path (one process per GPU): export the allocation holding `ptr`
+ * (64-byte handle + offset of `ptr` inside it), map a peer's allocation, unmap it.             */
+int qj_ipc_export(const void *ptr, void *handle64, int64_t *offset);
+int qj_ipc_open(const void *handle64, void **base_out);
+int qj_ipc_close(void *base);
 /* Staged variant for transports without peer mapping (NCCL send/recv of chunks):
  * pack: gather the half of `local` that leaves (bit m == 1 - is_upper) for amplitudes
  * [chunk_begin, chunk_begin + chunk_len) of the half-shard into contiguous `buf`;

@@ -45,6 +45,10 @@ SIGNATURES = {
     "qj_measure_frequencies": (_I, [_P, _P, _P, _I, _L, _I, _L, _I]),
     "qj_sample_shots": (_I, [_P, _P, _I, _I, _P, _L, _P, _P]),
     "qj_swap_pieces_peer": (_I, [_P, _P, _P, _I, _I, _I, _I]),
+    "qj_swap_bits_peer": (_I, [_P, _P, _P, _I, _I, _P, _I, _I, _I, _I, _I]),
+    "qj_ipc_export": (_I, [_P, _P, _c.POINTER(_L)]),
+    "qj_ipc_open": (_I, [_P, _c.POINTER(_P)]),
+    "qj_ipc_close": (_I, [_P]),
     "qj_swap_pack": (_I, [_P, _P, _P, _I, _I, _I, _I, _L, _L]),
     "qj_swap_unpack": (_I, [_P, _P, _P, _I, _I, _I, _I, _L, _L]),
     "qj_swap_pack_bits": (_I, [_P, _P, _P, _I, _I, _P, _I, _I, _L, _L]),

@@ -633,6 +633,90 @@ class B200Backend(_QiboBackend):
             self._stage_bufs[key] = buf
         return buf[:nelem]
 
+    # -- peer-memory transport (NVLink): every rank maps its peers' shards through CUDA IPC and a
+    #    swap kernel trades sub-blocks in place; the NCCL transport below stays as the fallback
+    #    (QJ_PEER_EXCHANGE=0, or IPC mapping not possible)
+    def _peer_pointers(self, shard, comm):
+        """{rank: device pointer to that rank's shard as seen from this process}, cached per shard."""
+        import ctypes
+
+        torch = _torch()
+        # every rank's current shard address: a cached mapping is valid only while NONE of them moved
+        # (states are re-allocated between circuit executions)
+        mine = torch.tensor([int(shard.data_ptr())], dtype=torch.int64, device=self.torch_device)
+        everyone = torch.empty(comm.world, dtype=torch.int64, device=self.torch_device)
+        comm.dist.all_gather_into_tensor(everyone, mine, group=comm.group)
+        key = tuple(everyone.cpu().tolist())
+        cache = self.__dict__.setdefault("_peer_cache", {})
+        if key in cache:
+            return cache[key]
+        handle = (ctypes.c_char * 64)()
+        off = ctypes.c_int64()
+        _capi.check(self._lib.qj_ipc_export(ctypes.c_void_p(shard.data_ptr()), handle, ctypes.byref(off)))
+        gathered = [None] * comm.world
+        comm.dist.all_gather_object(gathered, (bytes(handle.raw), int(off.value)), group=comm.group)
+        opened = self.__dict__.setdefault("_ipc_opened", {})
+        ptrs = {}
+        for r, (hb, o) in enumerate(gathered):
+            if r == comm.rank:
+                ptrs[r] = int(shard.data_ptr())
+                continue
+            if hb not in opened:
+                base = ctypes.c_void_p()
+                buf = ctypes.create_string_buffer(hb, 64)
+                _capi.check(self._lib.qj_ipc_open(buf, ctypes.byref(base)))
+                opened[hb] = int(base.value)
+            ptrs[r] = opened[hb] + o
+        cache[key] = ptrs
+        return ptrs
+
+    def release_peer_mappings(self):
+        """Unmap every peer shard (call on all ranks before the shards are freed: an allocation must
+        not be released while another process still maps it)."""
+        import ctypes
+
+        for base in self.__dict__.pop("_ipc_opened", {}).values():
+            self._lib.qj_ipc_close(ctypes.c_void_p(base))
+        self.__dict__.pop("_peer_cache", None)
+
+    def _peer_enabled(self, shard, comm):
+        import os
+
+        if os.environ.get("QJ_PEER_EXCHANGE", "1") == "0" or comm.world == 1:
+            return False
+        if getattr(self, "_peer_broken", False):
+            return False
+        try:
+            self._peer_pointers(shard, comm)
+            return True
+        except Exception as exc:          # IPC export / mapping not possible on this system
+            import sys
+
+            self._peer_broken = True
+            sys.stderr.write(f"qibojit_b200: peer-memory exchange unavailable ({exc}); using NCCL send/recv\n")
+            return False
+
+    def _stream_barrier(self, comm):
+        """Cross-rank barrier in stream order: nothing enqueued after it on any rank starts before
+        everything enqueued before it on every rank is done (no host synchronisation)."""
+        torch = _torch()
+        flag = self.__dict__.get("_barrier_flag")
+        if flag is None:
+            flag = self._barrier_flag = torch.zeros(1, dtype=torch.int32, device=self.torch_device)
+        comm.dist.all_reduce(flag, group=comm.group)
+
+    def _exchange_peer(self, shard, nlocal, lbits, pairs, comm):
+        """pairs: [(peer rank, my sub-block value, its sub-block value)] -- one swap kernel per peer,
+        this rank moves the half of the pair's amplitudes its rank order assigns to it."""
+        ptrs = self._peer_pointers(shard, comm)
+        bits = np.ascontiguousarray(np.asarray(lbits, dtype=np.int32))
+        tag, h = self._tag(shard), self._handle()
+        self._stream_barrier(comm)
+        for peer, mine_val, peer_val in pairs:
+            _capi.check(self._lib.qj_swap_bits_peer(h, shard.data_ptr(), ptrs[peer], tag, nlocal, bits.ctypes.data,
+                                                    len(lbits), mine_val, peer_val, 0 if comm.rank < peer else 1, 2))
+        self._stream_barrier(comm)
+
     def shard_exchange(self, shard, nlocal, lbit, peer, is_upper, comm, chunk_bytes=1 << 29):
         """Global<->local qubit swap with rank `peer` (ops.swap_pieces semantics): the amplitudes
         of this shard whose local bit `lbit` equals (1 - is_upper) are exchanged with the peer's
@@ -643,6 +727,9 @@ class B200Backend(_QiboBackend):
         dist = comm.dist
         half = 1 << (nlocal - 1)
         esize = shard.element_size()
+        if self._peer_enabled(shard, comm):
+            self._exchange_peer(shard, nlocal, [lbit], [(peer, 1 - int(is_upper), int(is_upper))], comm)
+            return half * esize
         chunk = max(2, min(half, chunk_bytes // esize))
         contiguous = lbit == nlocal - 1
         tag = self._tag(shard)
@@ -692,6 +779,11 @@ class B200Backend(_QiboBackend):
             peers[a] = r
         sub = 1 << (nlocal - k)
         esize = shard.element_size()
+        if self._peer_enabled(shard, comm):
+            # pairs meet in XOR-distance order: at step d this rank and its partner swap with each other
+            order = [mine ^ d for d in range(1, 1 << k)]
+            self._exchange_peer(shard, nlocal, list(lbits), [(peers[a], a, mine) for a in order], comm)
+            return len(others) * sub * esize
         # two chunk slots: chunk c + 1 is packed (and its transfers queued) while chunk c is on
         # the links, chunk c is unpacked while chunk c + 1 travels
         chunk = max(2, min(sub, (chunk_bytes // esize // len(others) // 2) & ~1023 or 2))   # whole 16-byte vectors

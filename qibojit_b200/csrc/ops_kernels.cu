@@ -498,6 +498,45 @@ k_swap_pack_bits(const float4 *__restrict__ local, float4 *__restrict__ buf, con
     }
 }
 
+// Multi-qubit exchange over peer memory (NVLink): this rank's sub-block `lmask` and the peer's
+// sub-block `pmask` trade places, element by element, with no staging buffer, no pack / unpack
+// pass and no library call in between: each of the two ranks of a pair runs this kernel on its
+// half of the groups, so both link directions carry reads and (posted) writes at once.
+// Four independent vector swaps per thread and iteration keep enough remote loads in flight.
+__global__ void __launch_bounds__(kThreads)
+k_swap_bits_peer(float4 *__restrict__ local, float4 *__restrict__ peer, const __grid_constant__ SubBlock sb,
+                 int64_t lmask, int64_t pmask, int64_t g_begin, int64_t g_end) {
+    const int64_t stride = int64_t(gridDim.x) * kThreads * 4;
+    for (int64_t g0 = g_begin + (int64_t(blockIdx.x) * kThreads + threadIdx.x) * 4; g0 < g_end; g0 += stride) {
+        int64_t idx[4];
+        float4 a[4], b[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            int64_t i = g0 + u;
+#pragma unroll 1
+            for (int j = 0; j < sb.npos; j++) {
+                const int p = sb.pos[j];
+                i = ((i >> p) << (p + 1)) | (i & ((int64_t(1) << p) - 1));
+            }
+            idx[u] = i;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            if (g0 + u < g_end) {
+                b[u] = peer[idx[u] | pmask];
+                a[u] = local[idx[u] | lmask];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            if (g0 + u < g_end) {
+                local[idx[u] | lmask] = b[u];
+                peer[idx[u] | pmask] = a[u];
+            }
+        }
+    }
+}
+
 template <typename F>
 int launch_checked(qj_handle *h, F &&f) {
     f();
@@ -888,6 +927,69 @@ int swap_pack_bits_impl(qj_handle *h, const void *local, void *buf, int dtype, i
     });
 }
 }  // namespace
+
+extern "C" int qj_swap_bits_peer(qj_handle *h, void *local, void *peer, int dtype, int nlocal, const int32_t *bits,
+                                 int nbits, int local_value, int peer_value, int part, int nparts) {
+    qj::DeviceGuard device_guard(h);
+    QJ_REQUIRE(h && local && peer && bits, "null argument");
+    QJ_REQUIRE(dtype == QJ_C64 || dtype == QJ_C128, "dtype must be QJ_C64 or QJ_C128");
+    QJ_REQUIRE(nbits >= 1 && nbits <= QJ_MAX_GLOBAL_SWAP && nbits < nlocal, "bad number of exchange bits");
+    QJ_REQUIRE(local_value >= 0 && local_value < (1 << nbits) && peer_value >= 0 && peer_value < (1 << nbits),
+               "sub-block value out of range");
+    QJ_REQUIRE(nparts >= 1 && part >= 0 && part < nparts, "bad part");
+    const int v = (dtype == QJ_C128) ? 0 : 1;
+    SubBlock sb;
+    sb.npos = nbits;
+    sb.ormask = 0;
+    int64_t lmask = 0, pmask = 0;
+    for (int i = 0; i < nbits; i++) {
+        if (bits[i] < v) return fail(QJ_ERR_UNSUPPORTED, "swap on index bit 0 of a complex64 shard: choose another local partner bit");
+        QJ_REQUIRE(bits[i] < nlocal && (i == 0 || bits[i] > bits[i - 1]), "exchange bits must be ascending and below nlocal");
+        sb.pos[i] = bits[i] - v;
+        if ((local_value >> i) & 1) lmask |= int64_t(1) << (bits[i] - v);
+        if ((peer_value >> i) & 1) pmask |= int64_t(1) << (bits[i] - v);
+    }
+    const int64_t ngroups = int64_t(1) << (nlocal - v - nbits);
+    const int64_t per = (ngroups + nparts - 1) / nparts;
+    const int64_t g_begin = std::min<int64_t>(ngroups, per * part), g_end = std::min<int64_t>(ngroups, per * (part + 1));
+    if (g_end <= g_begin) return QJ_OK;
+    return launch_checked(h, [&] {
+        k_swap_bits_peer<<<persistent_grid(h, (g_end - g_begin + 3) / 4, kThreads * 2), kThreads, 0, h->stream>>>(
+            reinterpret_cast<float4 *>(local), reinterpret_cast<float4 *>(peer), sb, lmask, pmask, g_begin, g_end);
+    });
+}
+
+// ---- CUDA IPC: a rank exports its shard allocation, its peers map it (one process per GPU)
+extern "C" int qj_ipc_export(const void *ptr, void *handle64, int64_t *offset) {
+    QJ_REQUIRE(ptr && handle64 && offset, "null argument");
+    // the allocation that holds `ptr` (torch's caching allocator hands out pieces of larger blocks)
+    typedef int (*range_fn)(unsigned long long *, size_t *, unsigned long long);
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    QJ_CUDA_OK(cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qres));
+    QJ_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, "cuMemGetAddressRange is not available");
+    unsigned long long base = 0;
+    size_t size = 0;
+    if (reinterpret_cast<range_fn>(fn)(&base, &size, (unsigned long long)(uintptr_t)ptr) != 0)
+        return fail(QJ_ERR_CUDA, "cuMemGetAddressRange failed");
+    cudaIpcMemHandle_t hd;
+    QJ_CUDA_OK(cudaIpcGetMemHandle(&hd, reinterpret_cast<void *>(uintptr_t(base))));
+    static_assert(sizeof(hd) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(handle64, &hd, 64);
+    *offset = int64_t((unsigned long long)(uintptr_t)ptr - base);
+    return QJ_OK;
+}
+extern "C" int qj_ipc_open(const void *handle64, void **base_out) {
+    QJ_REQUIRE(handle64 && base_out, "null argument");
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, handle64, 64);
+    QJ_CUDA_OK(cudaIpcOpenMemHandle(base_out, hd, cudaIpcMemLazyEnablePeerAccess));
+    return QJ_OK;
+}
+extern "C" int qj_ipc_close(void *base) {
+    if (base) QJ_CUDA_OK(cudaIpcCloseMemHandle(base));
+    return QJ_OK;
+}
 
 extern "C" int qj_swap_pack_bits(qj_handle *h, const void *local, void *buf, int dtype, int nlocal,
                                  const int32_t *bits, int nbits, int value, int64_t chunk_begin, int64_t chunk_len) {

@@ -616,7 +616,7 @@ class DistributedState:
         want = lambda bit: n - 1 - bit                      # logical qubit that belongs on `bit`
         steps = Plan()
         steps.initial_map = list(self.bit_of)
-        for _ in range(4 * max(1, self.nglobal)):
+        for _ in range(8 * max(1, self.nglobal) + 4):
             wrong = [p for p in range(nl, n) if self.bit_of[want(p)] != p]
             if not wrong:
                 break
@@ -627,17 +627,23 @@ class DistributedState:
                     pairs.append((self.qubit_at(p), q))
                     used.add(q)
             if not pairs:
-                # the wanted qubits sit on other rank bits (or on index bit 0 of a complex64
-                # shard): park one occupant on a local bit that nobody claims
-                p = wrong[0]
                 claimed = {want(b) for b in range(nl, n)}
+                low = [want(p) for p in wrong if self.bit_of[want(p)] == 0]
+                if low:
+                    # complex64 exchanges move 16-byte vectors: a wanted qubit on index bit 0 first
+                    # trades places with another local qubit (a local SWAP), then it can travel
+                    others = [v for v in range(n) if self.is_local(v) and v != low[0]]
+                    free = [v for v in others if v not in claimed] or others
+                    self._emit_move(steps, low[0], free[0])
+                    continue
+                # the wanted qubits sit on other rank bits: park one occupant on a local bit that
+                # nobody claims (breaks the cycle among the rank bits)
+                p = wrong[0]
                 victims = [v for v in range(n) if self.is_local(v) and v not in claimed
                            and not (self.dtype == "complex64" and self.bit_of[v] == 0)]
-                if not victims:     # tiny shards: move the complex64 bit-0 qubit up first
-                    low = self.qubit_at(0)
-                    other = next(v for v in range(n) if self.is_local(v) and v != low)
-                    self._emit_move(steps, low, other)
-                    continue
+                if not victims:
+                    victims = [v for v in range(n) if self.is_local(v)
+                               and not (self.dtype == "complex64" and self.bit_of[v] == 0)]
                 pairs = [(self.qubit_at(p), victims[0])]
             self._plan_multi_exchange(steps, pairs)
         else:
