@@ -506,13 +506,16 @@ k_swap_pack_bits(const float4 *__restrict__ local, float4 *__restrict__ buf, con
 __global__ void __launch_bounds__(kThreads)
 k_swap_bits_peer(float4 *__restrict__ local, float4 *__restrict__ peer, const __grid_constant__ SubBlock sb,
                  int64_t lmask, int64_t pmask, int64_t g_begin, int64_t g_end) {
-    const int64_t stride = int64_t(gridDim.x) * kThreads * 4;
-    for (int64_t g0 = g_begin + (int64_t(blockIdx.x) * kThreads + threadIdx.x) * 4; g0 < g_end; g0 += stride) {
-        int64_t idx[4];
-        float4 a[4], b[4];
+    // consecutive lanes take consecutive groups (whole 512-byte requests per warp, local and
+    // remote); the U groups of a thread are a whole grid apart
+    constexpr int U = 8;
+    const int64_t step = int64_t(gridDim.x) * kThreads;
+    for (int64_t g0 = g_begin + int64_t(blockIdx.x) * kThreads + threadIdx.x; g0 < g_end; g0 += step * U) {
+        int64_t idx[U];
+        float4 a[U], b[U];
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            int64_t i = g0 + u;
+        for (int u = 0; u < U; u++) {
+            int64_t i = g0 + u * step;
 #pragma unroll 1
             for (int j = 0; j < sb.npos; j++) {
                 const int p = sb.pos[j];
@@ -521,17 +524,16 @@ k_swap_bits_peer(float4 *__restrict__ local, float4 *__restrict__ peer, const __
             idx[u] = i;
         }
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            if (g0 + u < g_end) {
-                b[u] = peer[idx[u] | pmask];
-                a[u] = local[idx[u] | lmask];
-            }
-        }
+        for (int u = 0; u < U; u++)
+            if (g0 + u * step < g_end) b[u] = __ldcs(peer + (idx[u] | pmask));
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            if (g0 + u < g_end) {
-                local[idx[u] | lmask] = b[u];
-                peer[idx[u] | pmask] = a[u];
+        for (int u = 0; u < U; u++)
+            if (g0 + u * step < g_end) a[u] = __ldcs(local + (idx[u] | lmask));
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (g0 + u * step < g_end) {
+                __stcs(peer + (idx[u] | pmask), a[u]);
+                __stcs(local + (idx[u] | lmask), b[u]);
             }
         }
     }
@@ -954,7 +956,7 @@ extern "C" int qj_swap_bits_peer(qj_handle *h, void *local, void *peer, int dtyp
     const int64_t g_begin = std::min<int64_t>(ngroups, per * part), g_end = std::min<int64_t>(ngroups, per * (part + 1));
     if (g_end <= g_begin) return QJ_OK;
     return launch_checked(h, [&] {
-        k_swap_bits_peer<<<persistent_grid(h, (g_end - g_begin + 3) / 4, kThreads * 2), kThreads, 0, h->stream>>>(
+        k_swap_bits_peer<<<persistent_grid(h, g_end - g_begin, kThreads * 8), kThreads, 0, h->stream>>>(
             reinterpret_cast<float4 *>(local), reinterpret_cast<float4 *>(peer), sb, lmask, pmask, g_begin, g_end);
     });
 }

@@ -111,6 +111,14 @@ struct PassGeom {
     int nH;                // per-tile phase factors (outer-only parts of the phase groups)
     int nF;                // fused diagonals with an outer part (2^J per-tile, per-element factors each)
     int nFS;               // their slices in total (one table look-up per slice and tile)
+    // tile IO of the one-thread-per-16-vectors launch: vector u * nthreads + tid of the tile lives at
+    // global vector  tile base + thread part + io_goff[u]  and at shared vector  swz(tid) ^ io_soff[u]
+    // (the swizzle is XOR-linear, the run index splits into a thread and a per-iteration part):
+    // both per-iteration parts are launch constants, read as constant-bank operands
+    int64_t io_goff[16];
+    uint32_t io_soff[16];
+    int io_fast;           // the launch geometry satisfies the conditions above
+    int nrounds_smem;      // rounds whose per-thread constants are staged in shared memory
 };
 
 // ---- program image (16-byte units) -------------------------------------------------------------
@@ -691,7 +699,8 @@ k_pass(Cx<T> *__restrict__ state, const __grid_constant__ PassGeom pg, const Cx<
     uint4 *const s_H = prog + pg.prefix_units;                                      // one 16-byte slot per factor
     Cx<T> *const s_F = reinterpret_cast<Cx<T> *>(s_H + pg.nH);                      // N factors per fused diagonal
     uint4 *const s_FS = reinterpret_cast<uint4 *>(s_F + pg.nF * N);                 // one 16-byte slot per slice look-up
-    int64_t *const s_runoff = reinterpret_cast<int64_t *>(s_FS + pg.nFS);           // in vectors
+    uint2 *const s_rconst = reinterpret_cast<uint2 *>(s_FS + pg.nFS);               // [round][thread] {S, base}
+    int64_t *const s_runoff = reinterpret_cast<int64_t *>(s_rconst + pg.nrounds_smem * int(blockDim.x));   // in vectors
     int32_t *const s_outer = reinterpret_cast<int32_t *>(s_runoff + (1 << pg.nh));
     uint4 *const gvec = reinterpret_cast<uint4 *>(state);
 
@@ -714,10 +723,29 @@ k_pass(Cx<T> *__restrict__ state, const __grid_constant__ PassGeom pg, const Cx<
     const int nF = int(hdr1.z);
     const uint4 *const fents = prog + hdr1.w;
 
+    // a thread's place in the tile is the same in every tile: the shared-memory offset of its
+    // first register element (S) and its local position bits (base) are computed once per round
+    // for the whole launch
+    for (int rd = 0; rd < pg.nrounds_smem; rd++) {
+        const uint4 r1 = pp.u[rounds + 3 * rd + 1], r2 = pp.u[rounds + 3 * rd + 2];
+        const uint32_t tdw[4] = {r1.x, r1.y, r1.z, r1.w};
+        uint32_t S = 0, base = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            if ((tid >> k) & 1) {
+                S ^= (tdw[k >> 1] >> ((k & 1) * 16)) & 0xffffu;
+                base |= 1u << (((k < 4 ? r2.x : r2.y) >> ((k & 3) * 8)) & 255u);
+            }
+        }
+        s_rconst[rd * nthr + tid] = make_uint2(S, base);
+    }
+
     // (the launch uses exactly one thread per 16 vectors of the tile: every thread is live)
-    const bool fast_io = nthr >= 8 && nthr >= (1 << rv) && nvec == 16 * nthr;   // 16 vectors per thread
+    const bool fast_io = pg.io_fast != 0;
     const uint32_t sw_t = swz_vec(uint32_t(tid));
-    const int lane_off = tid & rvmask, run_t = tid >> rv, runs_per_iter = nthr >> rv;
+    const int lane_off = tid & rvmask, run_t = tid >> rv;
+    // this thread's part of every global vector address of the fast tile IO
+    const int64_t io_thr = fast_io ? int64_t(lane_off) + s_runoff[run_t] : 0;
 
     for (int64_t tile_id = blockIdx.x; tile_id < pg.ntiles; tile_id += gridDim.x) {
         // tile base: insert zeros at the high local bits
@@ -734,10 +762,9 @@ k_pass(Cx<T> *__restrict__ state, const __grid_constant__ PassGeom pg, const Cx<
         if (fast_io) {
             // vector u * nthr + tid: the swizzle is XOR-linear and nthr a multiple of the run length,
             // so the per-thread and the per-iteration (warp-uniform) parts separate
-            const uint4 *const gsrc = gvec + base_vec + lane_off;
+            const uint4 *const gsrc = gvec + base_vec + io_thr;
 #pragma unroll
-            for (int u = 0; u < 16; u++)
-                cp_async16(tilev + (sw_t ^ swz_vec(uint32_t(u * nthr))), gsrc + s_runoff[run_t + u * runs_per_iter]);
+            for (int u = 0; u < 16; u++) cp_async16(tilev + (sw_t ^ pg.io_soff[u]), gsrc + pg.io_goff[u]);
         } else {
             for (int lv = tid; lv < nvec; lv += nthr)
                 cp_async16(tilev + swz_vec(uint32_t(lv)), gvec + base_vec + s_runoff[lv >> rv] + (lv & rvmask));
@@ -795,18 +822,12 @@ k_pass(Cx<T> *__restrict__ state, const __grid_constant__ PassGeom pg, const Cx<
         // ---- rounds
 #pragma unroll 1
         for (int rd = 0; rd < nrounds; rd++) {
-            const uint4 r0 = pp.u[rounds + 3 * rd], r1 = pp.u[rounds + 3 * rd + 1], r2 = pp.u[rounds + 3 * rd + 2];
+            const uint4 r0 = pp.u[rounds + 3 * rd];
             {
                 uint32_t vd[4] = {r0.z & 0xffffu, r0.z >> 16, r0.w & 0xffffu, r0.w >> 16};
-                const uint32_t tdw[4] = {r1.x, r1.y, r1.z, r1.w};
-                uint32_t S = 0, base = 0;
-#pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    if ((tid >> k) & 1) {
-                        S ^= (tdw[k >> 1] >> ((k & 1) * 16)) & 0xffffu;
-                        base |= 1u << (((k < 4 ? r2.x : r2.y) >> ((k & 3) * 8)) & 255u);
-                    }
-                }
+                const uint2 rc = s_rconst[rd * nthr + tid];
+                uint32_t S = rc.x;
+                const uint32_t base = rc.y;
                 Cx<T> x[N];
 #pragma unroll
                 for (int v = 0; v < 16; v++) {
@@ -1040,14 +1061,14 @@ k_pass(Cx<T> *__restrict__ state, const __grid_constant__ PassGeom pg, const Cx<
 
         // ---- store the tile (four vectors in flight per thread)
         if (fast_io) {
-            uint4 *const gdst = gvec + base_vec + lane_off;
+            uint4 *const gdst = gvec + base_vec + io_thr;
 #pragma unroll
             for (int u0 = 0; u0 < 16; u0 += 4) {
                 uint4 q[4];
 #pragma unroll
-                for (int k = 0; k < 4; k++) q[k] = tilev[sw_t ^ swz_vec(uint32_t((u0 + k) * nthr))];
+                for (int k = 0; k < 4; k++) q[k] = tilev[sw_t ^ pg.io_soff[u0 + k]];
 #pragma unroll
-                for (int k = 0; k < 4; k++) gdst[s_runoff[run_t + (u0 + k) * runs_per_iter]] = q[k];
+                for (int k = 0; k < 4; k++) gdst[pg.io_goff[u0 + k]] = q[k];
             }
         } else {
 #pragma unroll 1
@@ -1280,7 +1301,24 @@ static int program_build(qj_handle *h, int dtype, int nqubits, const qj_pass_des
             L.geom.nH = int(h_units.size() / 4);
             L.geom.nF = int(f_dir.size());
             L.geom.nFS = int(f_slices.size());
+            L.geom.nrounds_smem = launch_rounds;
+            {   // constants of the fast tile IO (one thread per 16 vectors)
+                const int rv = geo.r - VS;
+                const int nvec = 1 << Tv;
+                const int nthr = std::max(1, std::min(kThreads, nvec >> kVecRegBits));
+                L.geom.io_fast = (nthr >= 8 && nthr >= (1 << rv) && nvec == 16 * nthr) ? 1 : 0;
+                for (int u = 0; u < 16; u++) {
+                    L.geom.io_soff[u] = swz_vec(uint32_t(u * nthr));
+                    int64_t off = 0;
+                    if (L.geom.io_fast) {
+                        const int run = (u * nthr) >> rv;     // the per-iteration part of the run index
+                        for (int b2 = 0; b2 < geo.nh; b2++) off |= int64_t((run >> b2) & 1) << (geo.hibit[b2] - VS);
+                    }
+                    L.geom.io_goff[u] = off;
+                }
+            }
             L.smem = (size_t(1) << Tv) * 16 + size_t(off_ops) * 16 + (h_units.size() / 4) * 16 + f_dir.size() * 256 + f_slices.size() * 16 +
+                     size_t(launch_rounds) * size_t(std::max(1, std::min(kThreads, (1 << Tv) >> kVecRegBits))) * 8 +
                      (size_t(8) << geo.nh) + (outer_units.size() / 2) * 4 + 16;
             prog->launches.push_back(L);
             blob_all.insert(blob_all.end(), img.begin(), img.end());

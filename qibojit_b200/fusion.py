@@ -52,18 +52,46 @@ def embed_apply(block, u, positions, k):
     return t.reshape(1 << k, cols)
 
 
+def _gate_key(gate):
+    """Value summary of a gate (class, qubits, parameters) for cache validation."""
+    def param(p):
+        if hasattr(p, "tobytes"):
+            a = np.ascontiguousarray(p)
+            return (a.shape, str(a.dtype), a.tobytes())
+        if isinstance(p, (list, tuple)):
+            return tuple(param(x) for x in p)
+        return repr(p)
+
+    key = (gate.__class__.__name__, tuple(gate.target_qubits), tuple(gate.control_qubits),
+           tuple(param(x) for x in getattr(gate, "parameters", ())))
+    if hasattr(gate, "gates"):
+        key += (tuple(_gate_key(g) for g in gate.gates),)
+    return key
+
+
 def fused_matrix(fgate, matrices):
-    """Dense matrix of a FusedGate over its ``target_qubits`` (qibo ``matrix_fused``)."""
-    if getattr(fgate, "_matrix", None) is not None:
-        return fgate._matrix
+    """Dense matrix of a FusedGate over its ``target_qubits`` (qibo ``matrix_fused``).
+
+    The product is built and cached in complex128 and cast to the asking backend's dtype on return
+    (a block first compiled under complex64 must not hand a float32-precision matrix to a later
+    complex128 program); the cache is keyed on the inner gates' parameters, so re-parametrising an
+    inner gate rebuilds it."""
+    key = tuple(_gate_key(g) for g in fgate.gates)
+    cached = getattr(fgate, "_matrix", None)
+    if cached is not None and getattr(fgate, "_matrix_key", None) == key:
+        return cached.astype(matrices.dtype)
+    from .matrices import CustomMatrices
+
+    wide = matrices if str(matrices.dtype) == "complex128" else CustomMatrices("complex128")
     bq = list(fgate.target_qubits)
     k = len(bq)
     block = np.eye(1 << k, dtype=np.complex128)
     for gate in fgate.gates:
         qs = list(gate.control_qubits) + list(gate.target_qubits)
-        block = embed_apply(block, full_matrix(gate, matrices), [bq.index(q) for q in qs], k)
-    fgate._matrix = block.astype(matrices.dtype)
-    return fgate._matrix
+        block = embed_apply(block, full_matrix(gate, wide), [bq.index(q) for q in qs], k)
+    fgate._matrix = block
+    fgate._matrix_key = key
+    return block.astype(matrices.dtype)
 
 
 def _fusable(gate):

@@ -194,3 +194,99 @@ def test_swap_pack_bits_roundtrip(dtype):
         barr = np.asarray([5, 3], dtype=np.int32)           # not ascending
         _capi.check(b._lib.qj_swap_pack_bits(b._handle(), shard.data_ptr(), shard.data_ptr(), tag, nlocal,
                                              barr.ctypes.data, 2, 0, 0, 2))
+
+
+SWAP_PIECES_CASES = [(3, 0), (3, 2), (5, 1), (9, 0), (9, 4), (9, 8)]     # (nlocal, new_global) of the golden generator
+
+
+def _swap_pieces_inputs(dtype):
+    """The golden generator's inputs (tests/golden/make_golden.py: seeds continue after the collapse cases)."""
+    seed = 1000 + 2 * len(cases.COLLAPSE)
+    out = []
+    for nlocal, new_global in SWAP_PIECES_CASES:
+        seed += 1
+        full = R.random_state(nlocal + 1, dtype, seed)
+        out.append((nlocal, new_global, full[: 1 << nlocal].copy(), full[1 << nlocal:].copy()))
+    return out
+
+
+@pytest.mark.parametrize("dtype", cases.DTYPES)
+@pytest.mark.parametrize("transport", ["pieces_peer", "bits_peer", "pack_unpack"])
+def test_swap_pieces_golden(transport, dtype, golden_ops):
+    """ops.swap_pieces (ops.py:131-137; pinned by the reference at tests/test_ops.py:168-233) through the
+    three device transports of a global<->local qubit swap: the in-place peer kernels
+    (`qj_swap_pieces_peer`, `qj_swap_bits_peer`; both pieces on this device play the two ranks) and
+    the pack -> transfer -> unpack path of the NCCL transport (`qj_swap_pack` / `qj_swap_unpack`).
+    Bit-exact against the reference's numba output."""
+    import torch
+
+    from qibojit_b200 import _capi
+
+    b = backend()
+    lib, h = b._lib, b._handle()
+    for nlocal, new_global, h0, h1 in _swap_pieces_inputs(dtype):
+        m = nlocal - new_global - 1
+        p0, p1 = b.cast(h0, dtype=dtype, copy=True), b.cast(h1, dtype=dtype, copy=True)
+        tag = b._tag(p0)
+        gold = golden_ops[f"swap_pieces|{dtype}|l{nlocal}|g{new_global}"]
+        if dtype == "complex64" and m == 0:
+            # 16-byte granularity: the planner never picks index bit 0 of a complex64 shard
+            with pytest.raises(NotImplementedError):
+                _capi.check(lib.qj_swap_pieces_peer(h, p0.data_ptr(), p1.data_ptr(), tag, nlocal, m, 0))
+            continue
+        if transport == "pieces_peer":
+            _capi.check(lib.qj_swap_pieces_peer(h, p0.data_ptr(), p1.data_ptr(), tag, nlocal, m, 0))
+            _capi.check(lib.qj_swap_pieces_peer(h, p1.data_ptr(), p0.data_ptr(), tag, nlocal, m, 1))
+        elif transport == "bits_peer":
+            bits = np.asarray([m], dtype=np.int32)
+            _capi.check(lib.qj_swap_bits_peer(h, p0.data_ptr(), p1.data_ptr(), tag, nlocal, bits.ctypes.data, 1, 1, 0, 0, 2))
+            _capi.check(lib.qj_swap_bits_peer(h, p1.data_ptr(), p0.data_ptr(), tag, nlocal, bits.ctypes.data, 1, 0, 1, 1, 2))
+        else:
+            half = 1 << (nlocal - 1)
+            s0 = torch.empty(half, dtype=p0.dtype, device=p0.device)
+            s1 = torch.empty(half, dtype=p0.dtype, device=p0.device)
+            cut = (half // 2) & ~1                                    # two chunks, vector aligned
+            for c0, n in ((0, cut), (cut, half - cut)):
+                if n == 0:
+                    continue
+                _capi.check(lib.qj_swap_pack(h, p0.data_ptr(), s0[c0:].data_ptr(), tag, nlocal, m, 0, c0, n))
+                _capi.check(lib.qj_swap_pack(h, p1.data_ptr(), s1[c0:].data_ptr(), tag, nlocal, m, 1, c0, n))
+            for c0, n in ((0, cut), (cut, half - cut)):
+                if n == 0:
+                    continue
+                _capi.check(lib.qj_swap_unpack(h, p0.data_ptr(), s1[c0:].data_ptr(), tag, nlocal, m, 0, c0, n))
+                _capi.check(lib.qj_swap_unpack(h, p1.data_ptr(), s0[c0:].data_ptr(), tag, nlocal, m, 1, c0, n))
+        got = np.concatenate([b.to_numpy(p0), b.to_numpy(p1)])
+        np.testing.assert_array_equal(got, gold, err_msg=f"{transport} nlocal={nlocal} new_global={new_global}")
+
+
+@pytest.mark.parametrize("dtype", cases.DTYPES)
+def test_swap_bits_peer_all_to_all(dtype):
+    """The multi-qubit exchange over peer memory: 2^k 'ranks' (all on this device) swap sub-blocks
+    pairwise; afterwards the k exchanged local bits and the k rank bits have traded places."""
+    from qibojit_b200 import _capi
+
+    b = backend()
+    lib, h = b._lib, b._handle()
+    nlocal, bits = 10, [3, 7, 9]
+    k = len(bits)
+    rng = np.random.default_rng(11)
+    host = [(rng.standard_normal(1 << nlocal) + 1j * rng.standard_normal(1 << nlocal)).astype(dtype) for _ in range(1 << k)]
+    dev = [b.cast(x, dtype=dtype, copy=True) for x in host]
+    tag = b._tag(dev[0])
+    barr = np.asarray(bits, dtype=np.int32)
+    for r in range(1 << k):
+        for d in range(1, 1 << k):
+            a = r ^ d
+            _capi.check(lib.qj_swap_bits_peer(h, dev[r].data_ptr(), dev[a].data_ptr(), tag, nlocal, barr.ctypes.data, k,
+                                              a, r, 0 if r < a else 1, 2))
+    idx = np.arange(1 << nlocal)
+    field = np.zeros_like(idx)
+    for i, l in enumerate(bits):
+        field |= ((idx >> l) & 1) << i
+    for r in range(1 << k):
+        want = host[r].copy()
+        for a in range(1 << k):
+            if a != r:
+                want[field == a] = host[a][field == r]
+        np.testing.assert_array_equal(b.to_numpy(dev[r]), want)
