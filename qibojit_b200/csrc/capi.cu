@@ -71,14 +71,18 @@ int fill_controls(GateCall &c, const int32_t *qubits, int nactive) {
 }
 
 int route_dense(qj_handle *h, const GateCall &c) {
-    if (c.ntargets > kMaxDirectTargets) {
-        if (h->route != 1 && tile_kernel_applies(h, c)) return launch_dense_tile(h, c);
-        return launch_dense_generic(h, c);
-    }
+    if (c.ntargets > kMaxDirectTargets) return launch_dense_generic(h, c);   // (the tile kernel stages at most 2^5 amplitudes per group)
     if (h->route == 2 && tile_kernel_applies(h, c)) return launch_dense_tile(h, c);
-    // automatic: measured on B200 (profiles/sweep_*.json) the register kernels are at or above
-    // the copy-bandwidth roofline for k <= 4 wherever the targets sit, so they are the default;
-    // the tile kernel stays selectable (route 2) for comparison and profiling.
+    // automatic: measured on B200 (profiles/r1_sweep_*.txt) the register kernels are at or above
+    // the copy-bandwidth roofline for k <= 4 wherever the targets sit -- except complex64 gates that
+    // act on index bit 0 (the two amplitudes of a 16-byte vector: the register kernel falls back to
+    // 8-byte accesses), where the TMA-staged tile kernel wins: k = 2 on bits {0,1} 5.86 vs 4.31 TB/s,
+    // k = 3 on {0,1,2} 3.81 vs 3.56, k = 4 on {0,1,2,3} 2.16 vs 1.96.  Those cases go to the tile kernel.
+    if (h->route == 0 && c.dtype == QJ_C64 && c.ntargets >= 2 && c.ntargets <= 4 && c.ncontrols == 0) {
+        bool bit0 = false;
+        for (int u = 0; u < c.ntargets; u++) bit0 |= c.tbits[u] == 0;
+        if (bit0 && tile_kernel_applies(h, c)) return launch_dense_tile(h, c);
+    }
     return launch_dense_direct(h, c);
 }
 

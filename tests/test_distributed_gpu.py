@@ -6,6 +6,7 @@ path is exercised by tools/dist_check.py under torchrun; its logs are under prof
 import numpy as np
 import pytest
 
+from oracle import oracle as O_
 from tests.gpu_utils import ATOL, backend
 from tests.test_distributed_cpu import _reference_state, _test_circuits
 
@@ -68,3 +69,52 @@ def test_measurement_leg_of_the_bench():
     out = bench.measurement_leg(b, state, n, "complex128", nshots=10 ** 6)
     assert out["nshots"] == 10 ** 6 and out["distinct_outcomes"] > 1000
     assert abs(out["norm_after_collapse"] - 1.0) < 1e-9
+
+
+@pytest.mark.parametrize("dtype", ["complex128", "complex64"])
+def test_single_rank_layout_and_measurement(dtype):
+    """The sharded state's layout / measurement functions on one rank (world size 1, CUDA kernels):
+    relabelled SWAPs leave a permuted qubit map, `to_tensor` undoes it ON THE DEVICE (a local segment
+    of SWAP gates compiled into passes), `collapse` and `sample_frequencies` agree with the
+    single-state backend (sampler: bit-exact).  The multi-rank versions run under torchrun
+    (tools/dist_check.py) and on gloo (tests/test_distributed_measure_cpu.py)."""
+    from qibojit_b200 import circuits, gates
+    from qibojit_b200.circuit import Circuit
+    from qibojit_b200.distributed import DistributedState, execute_distributed_circuit
+    from tests import refdispatch as R
+
+    b = backend()
+    b.set_dtype(dtype)
+    try:
+        n = 13
+        tol = ATOL[dtype]
+        c = Circuit(n)
+        c.add(circuits.qft(n).queue)
+        c.add([gates.RY(0, 0.3), gates.CNOT(0, n - 1), gates.SWAP(1, n - 2), gates.H(n - 1), gates.CU1(0, 2, 0.4),
+               gates.RX(1, 0.7), gates.SWAP(0, 2)])
+        ref = _reference_state(c, dtype)
+        ds = DistributedState(b, n, comm=_OneRank(), dtype=dtype)
+        ds.execute(c.queue)
+        assert ds.bit_of != [n - 1 - q for q in range(n)]
+        full = ds.to_tensor()
+        assert full.is_cuda and ds.bit_of == [n - 1 - q for q in range(n)]
+        np.testing.assert_allclose(b.to_numpy(full), ref, rtol=0, atol=tol)
+        np.random.seed(3)
+        f1 = ds.sample_frequencies(200000)
+        np.random.seed(3)
+        f2 = b.sample_frequencies(b.calculate_probabilities(full.clone(), list(range(n)), n), 200000)
+        assert sum(f1.values()) == 200000
+        assert dict(f1) == dict(f2)                # the single-state sampler on the same amplitudes: same chains
+        for qubits, shot in [([0, n - 1], 2), ([1], 1), ([0, 2, 3], 5)]:
+            d2 = DistributedState(b, n, comm=_OneRank(), dtype=dtype)
+            d2.execute(c.queue)
+            d2.collapse(qubits, shot)
+            want = R.collapse(O_, ref.copy(), qubits, shot, n, True)
+            np.testing.assert_allclose(d2.to_numpy_full(), want, rtol=0, atol=tol * 10)
+        init = R.random_state(n, dtype, 4)
+        d3 = execute_distributed_circuit(b, c, initial_state=init, comm=_OneRank())
+        np.testing.assert_allclose(b.to_numpy(d3.to_tensor()), R.reference_run(init, c.queue, n), rtol=0, atol=tol * 10)
+        with pytest.raises(TypeError):
+            execute_distributed_circuit(b, c, initial_state="zeros", comm=_OneRank())
+    finally:
+        b.set_dtype("complex128")

@@ -66,7 +66,7 @@ def main():
                          capture_output=True, text=True).stdout
     srows = list(csv.reader(src.splitlines()))
     starts = [i for i, r in enumerate(srows) if r and r[0] == "Kernel Name"]
-    if starts:
+    if starts and "Instructions Executed" in srows[starts[0] + 1]:     # (metrics-only captures have no source page)
         h2 = srows[starts[0] + 1]
         end = starts[1] if len(starts) > 1 else len(srows)
         body = [r for r in srows[starts[0] + 2:end] if len(r) == len(h2)]
@@ -84,12 +84,15 @@ def main():
             for op, n in byop.most_common(40):
                 f.write(f"{op:12s} {n:14d} {100 * n / tot:5.1f}%   samples {100 * samp[op] / max(1, tots):5.1f}%\n")
         print("wrote", args.out + "_sassmix.txt")
-    lines = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_lines.py"), args.report, args.kernel,
+    if not (starts and "Instructions Executed" in srows[starts[0] + 1]):
+        args.kernel = ""
+    lines = None if not args.kernel else subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_lines.py"), args.report, args.kernel,
                             "--launch", "0", "--top", "45", "--lib", args.lib] +
                            (["--units", str(args.units)] if args.units else []), capture_output=True, text=True)
-    with open(args.out + "_lines.txt", "w") as f:
-        f.write(lines.stdout + lines.stderr)
-    print("wrote", args.out + "_lines.txt")
+    if args.kernel:
+        with open(args.out + "_lines.txt", "w") as f:
+            f.write(lines.stdout + lines.stderr)
+        print("wrote", args.out + "_lines.txt")
 
     if args.traffic_key:
         ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
