@@ -335,7 +335,7 @@ def run_reference(args):
         line["configs0"] = qft20_cpu()
     except Exception as exc:
         line["configs0"] = {"error": str(exc)}
-    print(json.dumps(line))
+    emit(json.dumps(line))
 
 
 # --------------------------------------------------------------------------- GPU arm
@@ -571,7 +571,10 @@ def run_ours(args):
     if world > 1:
         from bench_distributed import run_distributed
 
-        return run_distributed(args, backend, world, rank)
+        line = run_distributed(args, backend, world, rank)
+        if line is not None:
+            emit(json.dumps(line))
+        return
 
     workload = args.workload or "qft"
     cfg = DEFAULTS[workload]
@@ -654,10 +657,36 @@ def run_ours(args):
         line["secondary"] = secondary
     if measurement is not None:
         line["measurement"] = measurement
-    print(json.dumps(line))
+    emit(json.dumps(line))
+
+
+class JsonStdout:
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version
+    banner from C): the process's file descriptor 1 is pointed at stderr for the whole run and the
+    line is written to the saved descriptor at the end."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.fd = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, line):
+        sys.stdout.flush()
+        os.write(self.fd, (line + "\n").encode())
+
+
+OUT = None
+
+
+def emit(line):
+    if OUT is not None:
+        OUT.emit(line)
+    else:
+        print(line)
 
 
 def main():
+    global OUT
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -673,6 +702,7 @@ def main():
                     help="append the measurement leg (probabilities, 10^6 shots, collapse); default for --workload qv")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    OUT = JsonStdout()
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)

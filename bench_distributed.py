@@ -246,6 +246,7 @@ def run_distributed(args, backend, world, rank):
             secondary[f"{name}-{n}"] = rec
             torch.cuda.empty_cache()
 
+    line = None
     if rank == 0:
         line = {
             "metric": "gates_per_second", "value": primary["value"], "unit": "gates/s", "n_gpus": world,
@@ -273,6 +274,6 @@ def run_distributed(args, backend, world, rank):
         }
         if secondary:
             line["secondary"] = secondary
-        print(json.dumps(line))
     dist.barrier()
     dist.destroy_process_group()
+    return line          # rank 0: the JSON line (bench.py writes it to the real stdout); other ranks: None
