@@ -92,8 +92,8 @@ def marginal_fixture(workload, nqubits, dtype):
 
 def ncu_traffic(workload, nqubits, dtype):
     """dram__bytes_read + dram__bytes_write per k_pass launch from the committed ncu capture of this
-    workload (profiles/r2_traffic.json, written by tools/ncu_traffic.py from the .ncu-rep)."""
-    path = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    workload (profiles/round2_traffic.json, written by tools/ncu_traffic.py from the .ncu-rep)."""
+    path = os.path.join(ROOT, "profiles", "round2_traffic.json")
     try:
         with open(path) as f:
             entry = json.load(f).get(f"{workload}-{nqubits}-{dtype}")

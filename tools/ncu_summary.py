@@ -9,7 +9,7 @@
   profiles/NAME_sassmix.txt    SASS instruction mix of the first launch (executed warp instructions
                                and stall samples per opcode)
   profiles/NAME_lines.txt      cost per source line (tools/ncu_lines.py) of the first launch
-  profiles/r2_traffic.json     with --traffic-key: dram bytes per launch (mean over the captured
+  profiles/round2_traffic.json     with --traffic-key: dram bytes per launch (mean over the captured
                                launches) for bench.py's roofline.traffic
 """
 
@@ -98,7 +98,7 @@ def main():
         ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
         scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Tbyte": 1e12}
         per = [float(r[ir]) * scale[units[ir]] + float(r[iw]) * scale[units[iw]] for r in data]
-        path = os.path.join(ROOT, "profiles", "r2_traffic.json")
+        path = os.path.join(ROOT, "profiles", "round2_traffic.json")
         try:
             store = json.load(open(path))
         except Exception:
