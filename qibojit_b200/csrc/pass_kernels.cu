@@ -90,6 +90,9 @@ enum {
     C_DIAGF = 40,     // fused diagonal: per-thread, per-element factors G[tid][unit] (x per-tile factors)
     C_DIAGC = 41,     // constant diagonal: one complex constant per selected unit, in the payload
     C_DIAGS = 42,     // slot-factorised diagonal: one factor per register slot and thread (x per-tile factor)
+    C_GROUP1H = 43,   // unnormalised Hadamard butterflies (s0 + s1, s0 - s1) on a set of slots: adds only; the
+                      // scale 2^(-1/2) of each is carried by the round's last Hadamard-like gate
+    C_DIAGCS = 44,    // + slot: constant diagonal over ALL elements with that register bit set (no mask tests)
 };
 
 // element selection of a C_PHASE op (which of a thread's register amplitudes the phase multiplies)
@@ -613,6 +616,42 @@ __device__ __forceinline__ void op_diags(Cx<T> (&x)[Lay<T>::N], const Cx<T> *__r
     }
 }
 
+// Unnormalised Hadamard on register slot A: (s0, s1) <- (s0 + s1, s0 - s1), adds only.
+template <typename T, int A>
+__device__ __forceinline__ void op_hadamard(Cx<T> (&x)[Lay<T>::N]) {
+    constexpr int N = Lay<T>::N;
+    if constexpr (A < Lay<T>::J) {
+#pragma unroll
+        for (int p = 0; p < N / 2; p++) {
+            const int e0 = insert0(p, A), e1 = e0 | (1 << A);
+            const Cx<T> a = x[e0], b = x[e1];
+            x[e0].re = a.re + b.re; x[e0].im = a.im + b.im;
+            x[e1].re = a.re - b.re; x[e1].im = a.im - b.im;
+        }
+    }
+}
+
+// Constant diagonal over the N / 2 elements whose register bit A is 1, one constant each (1 for the
+// elements the gates leave alone): straight-line code, no mask tests.
+template <typename T, int A>
+__device__ __forceinline__ void op_diagc_slot(Cx<T> (&x)[Lay<T>::N], const ProgParam &pp, int pay) {
+    constexpr int N = Lay<T>::N;
+    if constexpr (A < Lay<T>::J) {
+#pragma unroll
+        for (int p = 0; p < N / 2; p++) {
+            const int e = insert0(p, A) | (1 << A);
+            if constexpr (sizeof(T) == 8) {
+                const uint4 q = pp.u[pay + p];
+                cmul_inplace<T>(x[e], __hiloint2double(int(q.y), int(q.x)), __hiloint2double(int(q.w), int(q.z)));
+            } else {
+                const uint4 q = pp.u[pay + (p >> 1)];
+                if (p & 1) cmul_inplace<T>(x[e], __uint_as_float(q.z), __uint_as_float(q.w));
+                else cmul_inplace<T>(x[e], __uint_as_float(q.x), __uint_as_float(q.y));
+            }
+        }
+    }
+}
+
 // Constant diagonal: factors that depend on the register bits only (the phases between the H
 // gates of a QFT round, CZ / CU1 inside a register block): one complex constant per selected
 // 16-byte unit, read from the program image as uniform operands -- no memory traffic at all.
@@ -854,9 +893,45 @@ k_pass(Cx<T> *__restrict__ state, const __grid_constant__ PassGeom pg, const Cx<
                     int pay = op + 2;
                     op += int(h0.x >> 16);
                     const uint32_t code = h0.x & 0xffffu;
+                    if (code >= uint32_t(C_DIAGF)) {
+                        // the fused diagonals and butterflies: no predicates, their own short compare tree
+                        switch (code) {
+                        case C_DIAGF: {   // h0.y = F index (0xffff: none) | has_g << 16, h0.w = unit mask, h1.x = G
+                            const uint32_t fidx = h0.y & 0xffffu;
+                            const Cx<T> *const gp = tables + h1.x + tid * (VS ? 32 : 16);
+                            const bool full = h0.w == 0xffffu;
+                            if (fidx != 0xffffu) {
+                                if (full) op_diagf<T, true, true>(x, gp, h0.w, (h0.y >> 16) != 0u, s_F + fidx * N);
+                                else op_diagf<T, true, false>(x, gp, h0.w, (h0.y >> 16) != 0u, s_F + fidx * N);
+                            } else {
+                                if (full) op_diagf<T, false, true>(x, gp, h0.w, true, nullptr);
+                                else op_diagf<T, false, false>(x, gp, h0.w, true, nullptr);
+                            }
+                        } break;
+                        case C_DIAGC: op_diagc<T>(x, pp, pay, h0.w); break;
+                        case C_GROUP1H: {
+                            const uint32_t slots = h0.y >> 16;
+                            if (slots & 1u) op_hadamard<T, 0>(x);
+                            if (slots & 2u) op_hadamard<T, 1>(x);
+                            if (slots & 4u) op_hadamard<T, 2>(x);
+                            if (slots & 8u) op_hadamard<T, 3>(x);
+                            if (slots & 16u) op_hadamard<T, 4>(x);
+                        } break;
+#define QJ_DCS(A) op_diagc_slot<T, A>(x, pp, pay)
+                        QJ_SLOT_CASES(C_DIAGCS, QJ_DCS)
+#undef QJ_DCS
+                        case C_DIAGS: {   // h0.y = F index (0xffff: none) | has_g << 16, h0.w = slot mask, h1.x = G
+                            const uint32_t fidx = h0.y & 0xffffu;
+                            const Cx<T> *const gp = tables + h1.x + tid * (VS ? 8 : 4);
+                            if (fidx != 0xffffu) op_diags<T, true>(x, gp, h0.w, (h0.y >> 16) != 0u, s_F + fidx * N);
+                            else op_diags<T, false>(x, gp, h0.w, true, nullptr);
+                        } break;
+                        }
+                        continue;
+                    }
                     uint32_t emask = h0.w;
                     int oi = 0;
-                    if (code != C_PHASE && code < C_DIAGF && (h0.z != 0u || (h0.y & 0xffffu) != 0xffffu)) {   // predicated op
+                    if (code != C_PHASE && (h0.z != 0u || (h0.y & 0xffffu) != 0xffffu)) {   // predicated op
                         const uint32_t oslot = h0.y & 0xffffu, tmask = h0.z;
                         bool ok = (base & tmask) == tmask;
                         if (oslot != 0xffffu) {
@@ -990,25 +1065,6 @@ k_pass(Cx<T> *__restrict__ state, const __grid_constant__ PassGeom pg, const Cx<
                             emask = n0.w;
                             gcur = gnext;
                           }
-                        } break;
-                        case C_DIAGF: {   // h0.y = F index (0xffff: none) | has_g << 16, h0.w = unit mask, h1.x = G
-                            const uint32_t fidx = h0.y & 0xffffu;
-                            const Cx<T> *const gp = tables + h1.x + tid * (VS ? 32 : 16);
-                            const bool full = h0.w == 0xffffu;
-                            if (fidx != 0xffffu) {
-                                if (full) op_diagf<T, true, true>(x, gp, h0.w, (h0.y >> 16) != 0u, s_F + fidx * N);
-                                else op_diagf<T, true, false>(x, gp, h0.w, (h0.y >> 16) != 0u, s_F + fidx * N);
-                            } else {
-                                if (full) op_diagf<T, false, true>(x, gp, h0.w, true, nullptr);
-                                else op_diagf<T, false, false>(x, gp, h0.w, true, nullptr);
-                            }
-                        } break;
-                        case C_DIAGC: op_diagc<T>(x, pp, pay, h0.w); break;
-                        case C_DIAGS: {   // h0.y = F index (0xffff: none) | has_g << 16, h0.w = slot mask, h1.x = G
-                            const uint32_t fidx = h0.y & 0xffffu;
-                            const Cx<T> *const gp = tables + h1.x + tid * (VS ? 8 : 4);
-                            if (fidx != 0xffffu) op_diags<T, true>(x, gp, h0.w, (h0.y >> 16) != 0u, s_F + fidx * N);
-                            else op_diags<T, false>(x, gp, h0.w, true, nullptr);
                         } break;
                         default: {  // C_DIAGN: table index = outer part | fields of the base | element part
                             const int nf = int(h0.y >> 16);
@@ -1220,6 +1276,7 @@ static int program_build(qj_handle *h, int dtype, int nqubits, const qj_pass_des
     if (const char *ev = getenv("QJ_DIAGF_MIN")) fuse_min = atoi(ev);
     const bool generic_only = fuse_min >= 100;      // 100 + n: threshold n, never the slot-factorised form (tests)
     if (generic_only) fuse_min -= 100;
+    const bool hadamard_on = !generic_only && fuse_min > 0;   // (the same switch turns the butterfly form off)
 
     auto *prog = new qj_program();
     prog->dtype = dtype;
@@ -1479,19 +1536,37 @@ static int program_build(qj_handle *h, int dtype, int nqubits, const qj_pass_des
                         }
                         uint32_t um = 0;
                         std::vector<double> sc;
-                        for (int u = 0; u < 16; u++) {
-                            if (!((emu >> (u << VS)) & (VS ? 3u : 1u))) continue;
-                            um |= 1u << u;
-                            for (int j = 0; j < (1 << VS); j++) {
-                                const cd z = fac[size_t((u << VS) + j)];
-                                sc.push_back(z.real()); sc.push_back(z.imag());
+                        // every selected element has one register bit in common: the mask-free form
+                        // over the N / 2 elements with that bit set (constant 1 where nothing acts)
+                        int common = -1;
+                        if (!generic_only)
+                            for (int a = 0; a < J && common < 0; a++) {
+                                bool all = true;
+                                for (int e = 0; e < N; e++) if (((emu >> e) & 1u) && !((e >> a) & 1)) all = false;
+                                if (all) common = a;
+                            }
+                        uint32_t code_c = C_DIAGC;
+                        if (common >= 0) {
+                            code_c = uint32_t(C_DIAGCS + common);
+                            for (int p2 = 0; p2 < N / 2; p2++) {
+                                const int e = (((p2 >> common) << (common + 1)) | (p2 & ((1 << common) - 1))) | (1 << common);
+                                sc.push_back(fac[size_t(e)].real()); sc.push_back(fac[size_t(e)].imag());
+                            }
+                        } else {
+                            for (int u = 0; u < 16; u++) {
+                                if (!((emu >> (u << VS)) & (VS ? 3u : 1u))) continue;
+                                um |= 1u << u;
+                                for (int j = 0; j < (1 << VS); j++) {
+                                    const cd z = fac[size_t((u << VS) + j)];
+                                    sc.push_back(z.real()); sc.push_back(z.imag());
+                                }
                             }
                         }
                         std::vector<Unit> payload;
                         enc.push_scalars(payload, sc);
                         Unit h0, h1;
                         memset(&h1, 0, sizeof(h1));
-                        h0.w[0] = uint32_t(C_DIAGC) | (uint32_t(2 + payload.size()) << 16);
+                        h0.w[0] = code_c | (uint32_t(2 + payload.size()) << 16);
                         h0.w[1] = 0xffffu; h0.w[2] = 0; h0.w[3] = um;
                         r_ops.push_back(h0); r_ops.push_back(h1);
                         r_ops.insert(r_ops.end(), payload.begin(), payload.end());
@@ -1710,6 +1785,28 @@ static int program_build(qj_handle *h, int dtype, int nqubits, const qj_pass_des
                 pending.clear();
             };
 
+            // Hadamard-like gates a * [[1, 1], [1, -1]] without controls: all but the last one of the
+            // round run as add / subtract butterflies, the last one carries the product of the scales
+            // (a global factor commutes with everything in between)
+            auto hadamard_scale = [&](const qj_op_desc &od, double *a) -> bool {
+                if (od.kind != QJ_OPK_DENSE1 || od.ncontrols != 0 || od.ntargets != 1) return false;
+                if (od.data_offset < 0 || od.data_offset + 4 > ndata) return false;
+                const cd m0 = enc.data_at(od.data_offset), m1 = enc.data_at(od.data_offset + 1),
+                         m2 = enc.data_at(od.data_offset + 2), m3 = enc.data_at(od.data_offset + 3);
+                if (m0.imag() != 0.0 || m1.imag() != 0.0 || m2.imag() != 0.0 || m3.imag() != 0.0) return false;
+                if (m0.real() == 0.0 || m1.real() != m0.real() || m2.real() != m0.real() || m3.real() != -m0.real()) return false;
+                *a = m0.real();
+                return true;
+            };
+            int h_left = 0;
+            double round_scale = 1.0;
+            if (hadamard_on) {
+                for (int64_t oi = rdesc.first_op; oi < rdesc.first_op + rdesc.nops; oi++) {
+                    double a;
+                    if (hadamard_scale(ops[oi], &a)) h_left++;
+                }
+            }
+
             for (int64_t oi = rdesc.first_op; oi < rdesc.first_op + rdesc.nops; oi++) {
                 const qj_op_desc &od = ops[oi];
                 if (od.ncontrols < 0 || od.ncontrols > QJ_MAX_QUBITS) return bail("op: bad control count");
@@ -1749,6 +1846,20 @@ static int program_build(qj_handle *h, int dtype, int nqubits, const qj_pass_des
                     std::vector<cd> m(need);
                     for (int64_t i = 0; i < need; i++) m[i] = enc.data_at(od.data_offset + i);
                     std::vector<Unit> payload;
+                    double h_scale = 0.0;
+                    if (nt == 1 && h_left > 0 && hadamard_scale(od, &h_scale)) {
+                        h_left--;
+                        if (h_left > 0) {                 // not the last one: butterfly, scale deferred
+                            round_scale *= h_scale;
+                            const size_t at = r_ops.size();
+                            push_op(C_GROUP1H, oslot, 0, tmask, cmask_e, 0, nullptr, payload);
+                            r_ops[at].w[1] |= (1u << sl[0]) << 16;
+                            group_run.clear();
+                            continue;
+                        }
+                        for (cd &z : m) z *= round_scale;  // the last one: a real 2x2 with the accumulated scale
+                        round_scale = 1.0;
+                    }
                     if (nt == 1) {
                         bool real = true;
                         for (const cd &z : m) real = real && z.imag() == 0.0;

@@ -16,7 +16,7 @@ import numpy as np
 from qibojit_b200 import _capi, planner
 
 C_GROUP1C, C_GROUP1R, C_GROUP1X, C_PERM1, C_DENSE2, C_PERM2, C_PHASE, C_DIAGN = 0, 1, 2, 3, 8, 18, 28, 29
-C_DENSE2R, C_DIAGF, C_DIAGC, C_DIAGS = 30, 40, 41, 42
+C_DENSE2R, C_DIAGF, C_DIAGC, C_DIAGS, C_GROUP1H, C_DIAGCS = 30, 40, 41, 42, 43, 44
 SEL_ALL, SEL_SLOT, SEL_PAIR, SEL_MASK = 0, 1, 6, 16
 PAIRS = [(0, 1), (0, 2), (1, 2), (0, 3), (1, 3), (2, 3), (0, 4), (1, 4), (2, 4), (3, 4)]
 
@@ -199,7 +199,7 @@ def run_image(image, state):
                     op += units
                     emask = np.full(nthr, int(h0[3]), dtype=np.int64)
                     oi = 0
-                    if code not in (C_PHASE, C_DIAGF, C_DIAGC, C_DIAGS) and (int(h0[2]) != 0 or (int(h0[1]) & 0xffff) != 0xffff):
+                    if (code not in (C_PHASE, C_DIAGF, C_DIAGC, C_DIAGS) and not C_DIAGCS <= code < C_DIAGCS + 5) and (int(h0[2]) != 0 or (int(h0[1]) & 0xffff) != 0xffff):
                         oslot, tmask = int(h0[1]) & 0xffff, int(h0[2])
                         ok = (base & tmask) == tmask
                         if oslot != 0xffff:
@@ -320,6 +320,27 @@ def run_image(image, state):
                                     z = z * s_F[fidx, ee]
                                 x[:, ee] *= z
                         assert units == 2
+                    elif code == C_GROUP1H:
+                        slots = int(h0[1]) >> 16
+                        assert units == 2 and np.all(sel_e)          # plain gates only
+                        for A in range(J):
+                            if not (slots >> A) & 1:
+                                continue
+                            for e0 in range(N):
+                                if (e0 >> A) & 1:
+                                    continue
+                                e1 = e0 | (1 << A)
+                                s0, s1 = x[:, e0].copy(), x[:, e1].copy()
+                                x[:, e0] = s0 + s1                   # unnormalised: the scale rides on a later gate
+                                x[:, e1] = s0 - s1
+                    elif C_DIAGCS <= code < C_DIAGCS + 5:
+                        A = code - C_DIAGCS
+                        upe = 1 << VS
+                        assert units == 2 + (N // 2) // upe
+                        sc = image.scalars(U[pay:pay + (N // 2) // upe]).reshape(-1, 2)[:N // 2]
+                        for p2 in range(N // 2):
+                            ee = (((p2 >> A) << (A + 1)) | (p2 & ((1 << A) - 1))) | (1 << A)
+                            x[:, ee] *= sc[p2, 0] + 1j * sc[p2, 1]
                     elif code == C_DIAGS:
                         fidx, has_g, smask = int(h0[1]) & 0xffff, int(h0[1]) >> 16, int(h0[3])
                         per = 8 if VS else 4                        # factors per thread in the table
