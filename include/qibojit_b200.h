@@ -241,6 +241,13 @@ int qj_program_create(qj_handle *h, int dtype, int nqubits, const qj_pass_desc *
 int qj_program_run(qj_handle *h, const qj_program *p, void *state);
 /* one kernel launch of the program (bench/profiling: per-pass timing) */
 int qj_program_run_launch(qj_handle *h, const qj_program *p, void *state, int launch);
+/* Launches [first_launch, first_launch + nlaunches) (nlaunches < 0: to the end).  QJ_RUN_ZERO_INPUT:
+ * the state is |0...0> on entry and need not hold it -- the first of these launches writes every
+ * amplitude without reading any (`initial_state_vector`, ops.py:14-18, fused into the first pass:
+ * one state-sized write and one read less per circuit).                                          */
+#define QJ_RUN_ZERO_INPUT 1
+int qj_program_run_ex(qj_handle *h, const qj_program *p, void *state, int first_launch, int nlaunches,
+                      int flags);
 int qj_program_stats(const qj_program *p, int64_t *nlaunches, int64_t *nrounds, int64_t *nmops);
 int qj_program_destroy(qj_handle *h, qj_program *p);
 

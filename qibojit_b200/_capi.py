@@ -56,6 +56,7 @@ SIGNATURES = {
     "qj_program_create": (_I, [_P, _I, _I, _P, _I, _P, _L, _P, _L, _P, _L, _c.POINTER(_P)]),
     "qj_program_run": (_I, [_P, _P, _P]),
     "qj_program_run_launch": (_I, [_P, _P, _P, _I]),
+    "qj_program_run_ex": (_I, [_P, _P, _P, _I, _I, _I]),
     "qj_program_stats": (_I, [_P, _c.POINTER(_L), _c.POINTER(_L), _c.POINTER(_L)]),
     "qj_program_destroy": (_I, [_P, _P]),
     "qj_program_encode": (_I, [_I, _I, _P, _I, _P, _L, _P, _L, _P, _L, _c.POINTER(_P)]),
@@ -65,6 +66,7 @@ SIGNATURES = {
 }
 
 QJ_OPK_DENSE1, QJ_OPK_DENSE2, QJ_OPK_DIAG = 1, 2, 3
+QJ_RUN_ZERO_INPUT = 1
 QJ_MAX_DIAG_BITS, QJ_MAX_LOCAL_BITS, QJ_MAX_QUBITS, QJ_MAX_REG_BITS = 12, 16, 48, 8
 QJ_LAUNCH_INFO_FIELDS = 16
 

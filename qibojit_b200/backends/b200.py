@@ -830,13 +830,20 @@ class B200Backend(_QiboBackend):
         handful of passes over the state instead of one per gate; ``self.use_programs = False``
         restores the gate-by-gate loop of the reference."""
         nqubits = circuit.nqubits
+        programs = getattr(self, "use_programs", True) and nqubits >= 4 and len(circuit.queue) > 1
+        if initial_state is None and programs:
+            # from |0...0> the SWAP gates of the circuit are relabellings (planner.relabel_swaps_away)
+            # and the state preparation is fused into the first pass: the state starts as
+            # uninitialised memory that the first pass only writes
+            torch = _torch()
+            state = torch.empty(1 << nqubits, dtype=getattr(torch, str(self.dtype)), device=self.torch_device)
+            return self.compile_circuit(circuit, zero_state=True).run(state, from_zero=True)
         if initial_state is None:
             state = self.zero_state(nqubits)
         else:
             state = self.cast(initial_state, copy=True)
-        if getattr(self, "use_programs", True) and nqubits >= 4 and len(circuit.queue) > 1:
-            # from |0...0> the SWAP gates of the circuit are relabellings (planner.relabel_swaps_away)
-            return self.compile_circuit(circuit, zero_state=initial_state is None).run(state)
+        if programs:
+            return self.compile_circuit(circuit, zero_state=False).run(state)
         for gate in circuit.queue:
             state = gate.apply(self, state, nqubits)
         return state

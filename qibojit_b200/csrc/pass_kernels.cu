@@ -122,6 +122,7 @@ struct PassGeom {
     uint32_t io_soff[16];
     int io_fast;           // the launch geometry satisfies the conditions above
     int nrounds_smem;      // rounds whose per-thread constants are staged in shared memory
+    int zero_input;        // the input is |0...0>: the launch does not read the state (state preparation fused in)
 };
 
 // ---- program image (16-byte units) -------------------------------------------------------------
@@ -798,7 +799,16 @@ k_pass(Cx<T> *__restrict__ state, const __grid_constant__ PassGeom pg, const Cx<
         const int64_t base_vec = base_amp >> VS;
 
         // ---- load (asynchronous copies straight into the swizzled tile)
-        if (fast_io) {
+        if (pg.zero_input) {
+            // |0...0> input (ops.py:14-18 fused into the first pass): nothing to read -- the tile is zero
+            // except amplitude 0 of tile 0, which the thread that owns vector 0 sets after its own fill
+            const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+            for (int lv = tid; lv < nvec; lv += nthr) tilev[swz_vec(uint32_t(lv))] = zero;
+            if (tile_id == 0 && tid == 0) {
+                if constexpr (sizeof(T) == 8) *reinterpret_cast<double2 *>(tilev) = make_double2(1.0, 0.0);
+                else *reinterpret_cast<float4 *>(tilev) = make_float4(1.f, 0.f, 0.f, 0.f);
+            }
+        } else if (fast_io) {
             // vector u * nthr + tid: the swizzle is XOR-linear and nthr a multiple of the run length,
             // so the per-thread and the per-iteration (warp-uniform) parts separate
             const uint4 *const gsrc = gvec + base_vec + io_thr;
@@ -977,7 +987,7 @@ k_pass(Cx<T> *__restrict__ state, const __grid_constant__ PassGeom pg, const Cx<
                             // or 3 units: {table, nf | oslot << 16, tmask, f0} {f1..f4} {f5..f8}
                             const int ntab = int(h0.y & 0xffffu);
                             const uint32_t sel = h0.y >> 16;
-                            const bool allsign = h0.z != 0u;
+                            const bool allsign = (h0.z & 1u) != 0u;
                             int d = pay;
                             Cx<T> ph;
                             ph.re = T(1); ph.im = T(0);
@@ -991,6 +1001,7 @@ k_pass(Cx<T> *__restrict__ state, const __grid_constant__ PassGeom pg, const Cx<
                                 else ph = gcur;
                                 have = true;
                             }
+                            if (h0.z & 2u) sg ^= h1.w ^ (uint32_t(__popc(base & h1.z) & 1) << 31);   // parity sign: no table
                             if (h1.y != 0xffffffffu) {
                                 const Cx<T> z = *reinterpret_cast<const Cx<T> *>(s_H + h1.y);
                                 if (allsign) {
@@ -1384,6 +1395,8 @@ static int program_build(qj_handle *h, int dtype, int nqubits, const qj_pass_des
             launch_rounds = 0; launch_ops = 0;
         };
 
+        int h_left = 0;               // Hadamard-like gates of this pass still to come
+        double round_scale = 1.0;     // product of the scales the butterflies so far left out
         for (int64_t ri = pd.first_round; ri < pd.first_round + pd.nrounds; ri++) {
             const qj_round_desc &rdesc = rounds_in[ri];
             if (rdesc.nreg != J) return bail("round: need 4 (complex128) / 5 (complex64) register bits");
@@ -1719,6 +1732,8 @@ static int program_build(qj_handle *h, int dtype, int nqubits, const qj_pass_des
                     // thread-only slices -> one factor per thread, computed here: a thread's tile
                     // position (hence its index into each of these tables) is the same in every tile
                     uint32_t g_off = 0xffffffffu;
+                    bool parity = false;
+                    uint32_t parity_mask = 0, parity_sign = 0;
                     {
                         std::vector<cd> G;
                         for (size_t j : members) {
@@ -1732,6 +1747,28 @@ static int program_build(qj_handle *h, int dtype, int nqubits, const qj_pass_des
                                 uint32_t idx = 0;
                                 for (int f = 0; f < ps.nf; f++) idx |= host_field(base, ps.fields[f]);
                                 G[size_t(t)] *= ps.host[idx];
+                            }
+                        }
+                        // a +-1 factor that is the parity of some of the thread's position bits (any
+                        // product of Z / CZ / CCZ-free sign gates: (-1)^(popcount(base & M)) up to a
+                        // constant sign) needs no table: the kernel computes it from `base`
+                        if (!G.empty() && allsign && !generic_only) {
+                            uint32_t M = 0;
+                            bool ok = true;
+                            for (const cd &z : G) ok = ok && z.imag() == 0.0 && (z.real() == 1.0 || z.real() == -1.0);
+                            for (size_t kb = 0; ok && kb < tq.size(); kb++)
+                                if (G[size_t(1) << kb].real() != G[0].real()) M |= 1u << (tq[kb] + VS);
+                            for (int t = 0; ok && t < nthr_round; t++) {
+                                uint32_t base = 0;
+                                for (size_t kb = 0; kb < tq.size(); kb++) if ((t >> kb) & 1) base |= 1u << (tq[kb] + VS);
+                                const double want = G[0].real() * ((__builtin_popcount(base & M) & 1) ? -1.0 : 1.0);
+                                ok = G[size_t(t)].real() == want;
+                            }
+                            if (ok) {
+                                parity_mask = M;
+                                parity_sign = G[0].real() < 0.0 ? 0x80000000u : 0u;
+                                parity = true;
+                                G.clear();
                             }
                         }
                         if (!G.empty()) g_off = enc.push_table(G);
@@ -1774,10 +1811,12 @@ static int program_build(qj_handle *h, int dtype, int nqubits, const qj_pass_des
                     memset(&h1, 0, sizeof(h1));
                     h0.w[0] = uint32_t(C_PHASE) | (uint32_t(2 + payload.size()) << 16);
                     h0.w[1] = uint32_t(cross.size()) | (select_code(pending[i].emask) << 16);
-                    h0.w[2] = allsign ? 1u : 0u;
+                    h0.w[2] = (allsign ? 1u : 0u) | (parity ? 2u : 0u);
                     h0.w[3] = pending[i].emask;
                     h1.w[0] = g_off;
                     h1.w[1] = h_idx;
+                    h1.w[2] = parity_mask;      // sign = parity_sign ^ parity(base & parity_mask)
+                    h1.w[3] = parity_sign;
                     r_ops.push_back(h0); r_ops.push_back(h1);
                     r_ops.insert(r_ops.end(), payload.begin(), payload.end());
                     r_nops++;
@@ -1798,13 +1837,14 @@ static int program_build(qj_handle *h, int dtype, int nqubits, const qj_pass_des
                 *a = m0.real();
                 return true;
             };
-            int h_left = 0;
-            double round_scale = 1.0;
-            if (hadamard_on) {
-                for (int64_t oi = rdesc.first_op; oi < rdesc.first_op + rdesc.nops; oi++) {
-                    double a;
-                    if (hadamard_scale(ops[oi], &a)) h_left++;
-                }
+            if (hadamard_on && ri == pd.first_round) {      // counted over the whole pass: ONE gate carries the scale
+                h_left = 0;
+                round_scale = 1.0;
+                for (int64_t rj = pd.first_round; rj < pd.first_round + pd.nrounds; rj++)
+                    for (int64_t oi = rounds_in[rj].first_op; oi < rounds_in[rj].first_op + rounds_in[rj].nops; oi++) {
+                        double a;
+                        if (oi >= 0 && oi < nops && hadamard_scale(ops[oi], &a)) h_left++;
+                    }
             }
 
             for (int64_t oi = rdesc.first_op; oi < rdesc.first_op + rdesc.nops; oi++) {
@@ -2231,7 +2271,7 @@ extern "C" int qj_program_stats(const qj_program *p, int64_t *nlaunches, int64_t
 
 namespace {
 template <typename T>
-int launch_pass(qj_handle *h, const qj_program *p, void *state, int li) {
+int launch_pass(qj_handle *h, const qj_program *p, void *state, int li, int zero_input) {
     const qj_program::Launch &L = p->launches[li];
     static bool configured[kMaxDevices] = {false};   // the attribute is per device, not per process
     if (!configured[h->device]) {
@@ -2245,16 +2285,19 @@ int launch_pass(qj_handle *h, const qj_program *p, void *state, int li) {
     const int by_smem = (int)std::max<size_t>(1, (size_t(224) << 10) / (L.smem + 1024));
     const int per_sm = std::max(1, std::min(by_smem, 512 / threads));
     const unsigned grid = (unsigned)std::min<int64_t>(L.geom.ntiles, int64_t(h->sm_count) * per_sm);
+    PassGeom geom = L.geom;
+    geom.zero_input = zero_input;
     k_pass<T><<<grid, threads, L.smem, h->stream>>>(
-        reinterpret_cast<Cx<T> *>(state), L.geom, reinterpret_cast<const Cx<T> *>(p->d_tables), p->images[li]);
+        reinterpret_cast<Cx<T> *>(state), geom, reinterpret_cast<const Cx<T> *>(p->d_tables), p->images[li]);
     h->launches++;
     QJ_CUDA_OK(cudaGetLastError());
     return QJ_OK;
 }
 
-int run_launches(qj_handle *h, const qj_program *p, void *state, int first, int count) {
+int run_launches(qj_handle *h, const qj_program *p, void *state, int first, int count, int flags = 0) {
     for (int li = first; li < first + count; li++) {
-        const int rc = (p->dtype == QJ_C128) ? launch_pass<double>(h, p, state, li) : launch_pass<float>(h, p, state, li);
+        const int zero = (li == first) ? (flags & 1) : 0;
+        const int rc = (p->dtype == QJ_C128) ? launch_pass<double>(h, p, state, li, zero) : launch_pass<float>(h, p, state, li, zero);
         if (rc) return rc;
     }
     return QJ_OK;
@@ -2266,6 +2309,23 @@ extern "C" int qj_program_run(qj_handle *h, const qj_program *p, void *state) {
     QJ_REQUIRE(h && p && state, "null argument");
     QJ_REQUIRE((reinterpret_cast<uintptr_t>(state) & 15) == 0, "state must be 16-byte aligned");
     return run_launches(h, p, state, 0, (int)p->launches.size());
+}
+
+extern "C" int qj_program_run_ex(qj_handle *h, const qj_program *p, void *state, int first_launch, int nlaunches,
+                                 int flags) {
+    qj::DeviceGuard device_guard(h);
+    QJ_REQUIRE(h && p && state, "null argument");
+    QJ_REQUIRE((reinterpret_cast<uintptr_t>(state) & 15) == 0, "state must be 16-byte aligned");
+    if (nlaunches < 0) nlaunches = (int)p->launches.size() - first_launch;
+    QJ_REQUIRE(first_launch >= 0 && nlaunches >= 0 && first_launch + nlaunches <= (int)p->launches.size(),
+               "launch range out of bounds");
+    QJ_REQUIRE((flags & ~QJ_RUN_ZERO_INPUT) == 0, "unknown flag");
+    if (nlaunches == 0) {
+        // an empty program on |0...0> still has to prepare the state
+        if (flags & QJ_RUN_ZERO_INPUT) return qj_initial_state(h, state, p->dtype, p->nqubits);
+        return QJ_OK;
+    }
+    return run_launches(h, p, state, first_launch, nlaunches, flags);
 }
 
 extern "C" int qj_program_run_launch(qj_handle *h, const qj_program *p, void *state, int launch) {

@@ -658,33 +658,53 @@ class Program:
         if getattr(self, "closed", False):
             raise RuntimeError("this Program was closed (its device image is released): compile the circuit again")
 
-    def run(self, state):
+    def _prepare_zero(self, state):
+        """|0...0> by the initial-state kernel (when the first segment is not a pass program that
+        can fuse the preparation in)."""
+        b = self.backend
+        _capi.check(b._lib.qj_initial_state(b._handle(), state.data_ptr(), b._tag(state), self.nqubits))
+
+    def run(self, state, from_zero=False):
+        """Apply the program to `state` in place.  `from_zero`: the input is |0...0> and `state` need
+        not hold it (it may be uninitialised memory): the first pass writes every amplitude without
+        reading any -- `initial_state_vector` (ops.py:14-18) fused into the first pass."""
         b = self.backend
         self._check_open()
         if state.numel() != (1 << self.nqubits) or str(state.dtype).replace("torch.", "") != self.dtype:
             raise ValueError("state does not match the program's qubit count / dtype")
+        if from_zero and not (self.segments and self.segments[0][0] == "program"):
+            self._prepare_zero(state)
+            from_zero = False
         for seg in self.segments:
             if seg[0] == "program":
-                _capi.check(b._lib.qj_program_run(b._handle(), seg[1], state.data_ptr()))
+                flags = _capi.QJ_RUN_ZERO_INPUT if from_zero else 0
+                from_zero = False
+                _capi.check(b._lib.qj_program_run_ex(b._handle(), seg[1], state.data_ptr(), 0, -1, flags))
             else:
                 state = seg[1].apply(b, state, self.nqubits)
         return state
 
-    def run_timed(self, state, timer):
+    def run_timed(self, state, timer, from_zero=False):
         """Like run(), but every kernel launch goes through ``timer(kind, fraction, fn)`` where
         `fraction` is the launch's algorithmic traffic in units of one full read+write of the
-        state -- bench.py brackets `fn` with CUDA events."""
+        state -- bench.py brackets `fn` with CUDA events.  A pass that
+        starts from |0...0> (`from_zero`) only writes: fraction 0.5."""
         from .backends.b200 import GATE_OPS
 
         b = self.backend
         self._check_open()
+        if from_zero and not (self.segments and self.segments[0][0] == "program"):
+            timer("init", 0.5, lambda: self._prepare_zero(state))
+            from_zero = False
         for seg in self.segments:
             if seg[0] == "program":
                 a = ctypes.c_int64()
                 _capi.check(b._lib.qj_program_stats(seg[1], ctypes.byref(a), None, None))
                 for i in range(a.value):
-                    timer("pass", 1.0, lambda i=i: _capi.check(
-                        b._lib.qj_program_run_launch(b._handle(), seg[1], state.data_ptr(), i)))
+                    flags = _capi.QJ_RUN_ZERO_INPUT if (from_zero and i == 0) else 0
+                    timer("pass0" if flags else "pass", 0.5 if flags else 1.0, lambda i=i, flags=flags: _capi.check(
+                        b._lib.qj_program_run_ex(b._handle(), seg[1], state.data_ptr(), i, 1, flags)))
+                from_zero = False
             else:
                 g = seg[1]
                 c = len(g.control_qubits)

@@ -266,12 +266,17 @@ def run_image(image, state):
                             s = x[m][:, idx]
                             x[np.ix_(np.nonzero(m)[0], idx)] = s @ g.T
                     elif code == C_PHASE:
-                        ntab, sel, allsign = int(h0[1]) & 0xffff, int(h0[1]) >> 16, int(h0[2])
+                        ntab, sel, allsign = int(h0[1]) & 0xffff, int(h0[1]) >> 16, int(h0[2]) & 1
+                        parity = (int(h0[2]) >> 1) & 1
                         ph = np.ones(nthr, dtype=np.complex128)
                         if int(h1[0]) != 0xffffffff:
                             ph = ph * image.tables[int(h1[0]) + tid]
                         if int(h1[1]) != 0xffffffff:
                             ph = ph * s_H[int(h1[1])]
+                        if parity:          # sign = constant sign x parity of some position bits of the thread
+                            assert allsign and int(h1[0]) == 0xffffffff
+                            par = np.array([bin(int(v) & int(h1[2])).count("1") & 1 for v in base])
+                            ph = ph * np.where(par == 1, -1.0, 1.0) * (-1.0 if int(h1[3]) else 1.0)
                         d = pay
                         for _ in range(ntab):
                             d0, d1 = U[d], U[d + 1]

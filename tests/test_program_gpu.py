@@ -164,3 +164,35 @@ def test_zero_state_program_relabels_swaps(seed, dtype):
         np.testing.assert_allclose(out, R.reference_run(rs, glist, n), rtol=0, atol=atol)
     finally:
         b.set_dtype("complex128")
+
+
+@pytest.mark.parametrize("dtype", ["complex128", "complex64"])
+@pytest.mark.parametrize("n", [8, 13, 17])
+def test_program_from_zero_ignores_the_buffer(n, dtype):
+    """`run(state, from_zero=True)`: |0...0> preparation (ops.py:14-18) fused into the first pass -- the
+    first launch writes every amplitude without reading any, so garbage in the buffer must not matter;
+    a program whose first segment is a raw gate falls back to the initial-state kernel."""
+    import torch
+
+    b = backend()
+    b.set_dtype(dtype)
+    try:
+        for seed, head in ((1, []), (2, [gates.Unitary(R.random_unitary(8, 3), 0, 1, 2)])):     # raw 3-qubit gate first
+            glist = head + random_circuit_gates(n, 50, seed + n)
+            st = np.zeros(1 << n, dtype=dtype)
+            st[0] = 1
+            ref = R.reference_run(st, glist, n)
+            prog = planner.Program(b, glist, n, dtype=dtype)
+            garbage = torch.full((1 << n,), float("nan"), dtype=getattr(torch, dtype), device=b.torch_device)
+            out = b.to_numpy(prog.run(garbage, from_zero=True))
+            np.testing.assert_allclose(out, ref, rtol=0, atol=ATOL[dtype])
+            want = b.to_numpy(prog.run(b.cast(st, dtype=dtype, copy=True)))
+            np.testing.assert_array_equal(out, want)           # bit-identical to the explicit preparation
+            prog.close()
+        # an empty program still prepares the state
+        prog = planner.Program(b, [], n, dtype=dtype)
+        garbage = torch.full((1 << n,), float("nan"), dtype=getattr(torch, dtype), device=b.torch_device)
+        out = b.to_numpy(prog.run(garbage, from_zero=True))
+        assert out[0] == 1 and not np.any(out[1:])
+    finally:
+        b.set_dtype("complex128")
