@@ -87,7 +87,48 @@ def _check_parity(state, workload, nqubits, dtype, dist):
     return out
 
 
-def time_sharded(backend, workload, nqubits, dtype, steps, warmup, world, rank):
+def measurement_leg_sharded(state, nqubits, dtype, nshots=10 ** 6):
+    """BASELINE.json configs[4] on a sharded state: layout normalisation + full-register
+    probabilities (all-gathered), 10^6-shot sampling with the reference's Metropolis sampler
+    semantics (ops.py:86-108; every rank runs the same chains on the gathered vector) and one
+    collapse on three qubits (local zeroing / rank predicate, all-reduced norm, rescale).  Each
+    part is timed with CUDA events on the launch stream, max over ranks."""
+    import torch
+    import torch.distributed as dist
+
+    def timed(fn):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0.record()
+        out = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return out, float(ms[0])
+
+    np.random.seed(123)
+    probs, ms_probs = timed(state.full_probabilities)
+    freqs, ms_sample = timed(lambda: state.backend.sample_frequencies(probs, nshots))
+    assert sum(freqs.values()) == nshots, sum(freqs.values())
+    del probs
+    torch.cuda.empty_cache()
+    shot = max(freqs, key=freqs.get)
+    qubits = [1, nqubits // 2, nqubits - 2]
+    outcome = sum(((shot >> (nqubits - 1 - q)) & 1) << (len(qubits) - 1 - i) for i, q in enumerate(qubits))
+    _, ms_collapse = timed(lambda: state.collapse(qubits, outcome))
+    norm2 = state.norm2()
+    assert abs(norm2 - 1.0) < (1e-9 if dtype == "complex128" else 1e-4), norm2
+    return {"nshots": nshots, "distinct_outcomes": len(freqs),
+            "layout_and_probabilities_ms": ms_probs, "sample_frequencies_ms": ms_sample,
+            "shots_per_second": nshots / (ms_sample * 1e-3), "collapse_qubits": qubits, "collapse_ms": ms_collapse,
+            "norm2_after_collapse": norm2,
+            "note": "probabilities: device-side layout normalisation (exchange + local SWAP passes), |amp|^2 and an "
+                    "all-gather of 2^n reals to every rank; the sampler then runs on every rank (same seed, same result)"}
+
+
+def time_sharded(backend, workload, nqubits, dtype, steps, warmup, world, rank, measure=False):
     """Plan once, then time `steps` executions of the sharded circuit (device events, max over
     ranks).  Returns the record (same fields as bench.time_program) on every rank."""
     import torch
@@ -153,6 +194,10 @@ def time_sharded(backend, workload, nqubits, dtype, steps, warmup, world, rank):
                  for k, v in per_kind.items()}
     stats = dict(state.stats)
     parity = _check_parity(state, workload, nqubits, dtype, dist)
+    measurement = None
+    if measure:
+        state.backend = backend          # (untimed proxy off: the leg brackets its own parts)
+        measurement = measurement_leg_sharded(state, nqubits, dtype)
     h2d = sum(st.compiled.upload_bytes for st in steps_plan if isinstance(st, LocalSegment) and st.compiled is not None)
     record = {
         "workload": f"{workload}-{nqubits}-{dtype}", "circuit_gates": ngates, "n_gpus": world,
@@ -169,6 +214,8 @@ def time_sharded(backend, workload, nqubits, dtype, steps, warmup, world, rank):
                      "exchange_note": "exchange GB/s = bytes sent per rank / time; NVLink reference 770 GB/s per direction"},
         "parity": parity, "clocks": clocks.summary(),
     }
+    if measurement is not None:
+        record["measurement"] = measurement
     torch.cuda.synchronize()
     dist.barrier()
     backend.release_peer_mappings()        # before any rank frees its shard
@@ -226,7 +273,8 @@ def run_distributed(args, backend, world, rank):
     nqubits = args.nqubits or cfg["nqubits"]
     dtype = args.dtype or cfg["dtype"]
 
-    primary, circuit = time_sharded(backend, workload, nqubits, dtype, args.steps, args.warmup, world, rank)
+    primary, circuit = time_sharded(backend, workload, nqubits, dtype, args.steps, args.warmup, world, rank,
+                                    measure=(workload == "qv" or args.measure))
     e2e = time_sharded_e2e(backend, circuit, nqubits, dtype, min(args.steps, 2))
     e2e["h2d_bytes_per_step"] = primary["program_upload_bytes"]
     torch.cuda.empty_cache()
@@ -274,6 +322,8 @@ def run_distributed(args, backend, world, rank):
         }
         if secondary:
             line["secondary"] = secondary
+        if "measurement" in primary:
+            line["measurement"] = primary["measurement"]
     dist.barrier()
     dist.destroy_process_group()
     return line          # rank 0: the JSON line (bench.py writes it to the real stdout); other ranks: None
