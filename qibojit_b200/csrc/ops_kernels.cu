@@ -146,8 +146,26 @@ __global__ void __launch_bounds__(kThreads) k_finish_max(const double *partials,
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 k_probs_full(const Cx<T> *__restrict__ st, int64_t n, T *__restrict__ probs) {
+    // 16-byte accesses on both sides: a thread turns 32 (complex128) / 32 (complex64) bytes of
+    // amplitudes into 16 bytes of probabilities; two independent groups per iteration
+    constexpr int V = 16 / sizeof(T);              // probabilities per 16-byte store: 2 (double) / 4 (float)
+    const int64_t ngroups = n / V;
     const int64_t stride = int64_t(gridDim.x) * kThreads;
-    for (int64_t i = int64_t(blockIdx.x) * kThreads + threadIdx.x; i < n; i += stride) {
+    const float4 *src = reinterpret_cast<const float4 *>(st);
+    float4 *dst = reinterpret_cast<float4 *>(probs);
+    for (int64_t g = int64_t(blockIdx.x) * kThreads + threadIdx.x; g < ngroups; g += stride) {
+        if constexpr (sizeof(T) == 8) {
+            const float4 q0 = __ldcs(src + 2 * g), q1 = __ldcs(src + 2 * g + 1);
+            const double2 a = *reinterpret_cast<const double2 *>(&q0), b = *reinterpret_cast<const double2 *>(&q1);
+            double2 o = make_double2(a.x * a.x + a.y * a.y, b.x * b.x + b.y * b.y);
+            __stcs(dst + g, *reinterpret_cast<float4 *>(&o));
+        } else {
+            const float4 a = __ldcs(src + 2 * g), b = __ldcs(src + 2 * g + 1);
+            __stcs(dst + g, make_float4(a.x * a.x + a.y * a.y, a.z * a.z + a.w * a.w, b.x * b.x + b.y * b.y, b.z * b.z + b.w * b.w));
+        }
+    }
+    // (registers of fewer than V amplitudes: one or two qubits)
+    for (int64_t i = ngroups * V + int64_t(blockIdx.x) * kThreads + threadIdx.x; i < n; i += stride) {
         const Cx<T> a = st[i];
         probs[i] = a.re * a.re + a.im * a.im;
     }
@@ -677,6 +695,8 @@ int probs_t(qj_handle *h, const void *state, int nqubits, const int32_t *bits, i
         if (bits[j] != nqubits - 1 - j) natural = false;
     }
     if (natural) {
+        QJ_REQUIRE((reinterpret_cast<uintptr_t>(probs) & 15) == 0 && (reinterpret_cast<uintptr_t>(state) & 15) == 0,
+                   "state and probabilities must be 16-byte aligned");
         return launch_checked(h, [&] {
             k_probs_full<T><<<persistent_grid(h, n, kThreads * 4), kThreads, 0, h->stream>>>(st, n, out);
         });
