@@ -248,6 +248,15 @@ int qj_program_run_launch(qj_handle *h, const qj_program *p, void *state, int la
 #define QJ_RUN_ZERO_INPUT 1
 int qj_program_run_ex(qj_handle *h, const qj_program *p, void *state, int first_launch, int nlaunches,
                       int flags);
+/* One launch restricted to the tiles [tile_begin, tile_begin + tile_count): a caller that knows a
+ * sub-block of the state is complete (the distributed layer pipelines the last pass before a qubit
+ * exchange against the exchange itself, sub-block by sub-block) runs the pass on that sub-block
+ * alone.  Tiles are numbered by the index bits outside the tile, least significant first;
+ * `qj_program_launch_geometry` fills out[0..11] = {tile bits, run bits, high tile bits, number of
+ * tiles, the high tile bits' index bits (8 entries, -1 = unused)}.                             */
+int qj_program_run_tiles(qj_handle *h, const qj_program *p, void *state, int launch, int64_t tile_begin,
+                         int64_t tile_count);
+int qj_program_launch_geometry(const qj_program *p, int launch, int64_t *out);
 int qj_program_stats(const qj_program *p, int64_t *nlaunches, int64_t *nrounds, int64_t *nmops);
 int qj_program_destroy(qj_handle *h, qj_program *p);
 

@@ -57,6 +57,8 @@ SIGNATURES = {
     "qj_program_run": (_I, [_P, _P, _P]),
     "qj_program_run_launch": (_I, [_P, _P, _P, _I]),
     "qj_program_run_ex": (_I, [_P, _P, _P, _I, _I, _I]),
+    "qj_program_run_tiles": (_I, [_P, _P, _P, _I, _L, _L]),
+    "qj_program_launch_geometry": (_I, [_P, _I, _P]),
     "qj_program_stats": (_I, [_P, _c.POINTER(_L), _c.POINTER(_L), _c.POINTER(_L)]),
     "qj_program_destroy": (_I, [_P, _P]),
     "qj_program_encode": (_I, [_I, _I, _P, _I, _P, _L, _P, _L, _P, _L, _c.POINTER(_P)]),

@@ -717,6 +717,98 @@ class B200Backend(_QiboBackend):
                                                     len(lbits), mine_val, peer_val, 0 if comm.rank < peer else 1, 2))
         self._stream_barrier(comm)
 
+    def run_segment_then_exchange(self, shard, nlocal, segment, lbits, rank_bits, rank, comm, chunk_bytes=1 << 29):
+        """A local segment followed by the exchange of `lbits` <-> `rank_bits`, with the LAST pass of
+        the segment pipelined against the exchange over peer memory: that pass runs sub-block by
+        sub-block (XOR order: at step d this rank finishes the sub-block it trades with the rank at
+        distance d, which finishes its counterpart at the same step), and the swap of step d runs on
+        a side stream while the pass works on the sub-block of step d + 1.  Falls back to "segment,
+        then exchange" whenever the geometry does not allow it (exchanged bits inside the pass's tile
+        or not the shard's top bits, NCCL transport, gate-by-gate execution).  Returns (shard, bytes sent)."""
+        import ctypes
+        import os
+
+        torch = _torch()
+        k = len(lbits)
+        esize = shard.element_size()
+        moved = ((1 << k) - 1) * (1 << (nlocal - k)) * esize
+
+        def plain():
+            out = self.run_local_segment(shard, nlocal, segment)
+            if k == 1:
+                peer = rank ^ (1 << rank_bits[0])
+                self.shard_exchange(out, nlocal, lbits[0], peer, (rank >> rank_bits[0]) & 1, comm, chunk_bytes)
+            else:
+                self.shard_exchange_multi(out, nlocal, lbits, rank_bits, rank, comm, chunk_bytes)
+            return out, moved
+
+        if (os.environ.get("QJ_OVERLAP_EXCHANGE", "1") == "0" or not getattr(self, "overlap_exchange", True)
+                or not getattr(self, "use_programs", True) or not self._peer_enabled(shard, comm)):
+            return plain()
+        if segment.compiled is None:
+            from ..planner import Program
+
+            segment.compiled = Program(self, segment.gates, nlocal, dtype=str(shard.dtype).replace("torch.", ""))
+        prog = segment.compiled
+        if not prog.segments or prog.segments[-1][0] != "program" or list(lbits) != list(range(nlocal - k, nlocal)):
+            return plain()
+        handle = prog.segments[-1][1]
+        nl = ctypes.c_int64()
+        _capi.check(self._lib.qj_program_stats(handle, ctypes.byref(nl), None, None))
+        last = int(nl.value) - 1
+        geom = (ctypes.c_int64 * 12)()
+        _capi.check(self._lib.qj_program_launch_geometry(handle, last, geom))
+        ntiles, hibits = int(geom[3]), [int(v) for v in geom[4:12] if v >= 0]
+        if last < 0 or any(b in hibits for b in lbits) or int(geom[1]) > nlocal - k or ntiles % (1 << k):
+            return plain()
+
+        self.overlapped_exchanges = getattr(self, "overlapped_exchanges", 0) + 1
+        h = self._handle()
+        ptr = shard.data_ptr()
+        for seg in prog.segments[:-1]:
+            if seg[0] == "program":
+                _capi.check(self._lib.qj_program_run(h, seg[1], ptr))
+            else:
+                seg[1].apply(self, shard, nlocal)
+        if last > 0:
+            _capi.check(self._lib.qj_program_run_ex(h, handle, ptr, 0, last, 0))
+        ptrs = self._peer_pointers(shard, comm)
+        main = torch.cuda.current_stream(self._device_index)
+        side = self.__dict__.get("_side_stream")
+        if side is None:
+            side = self._side_stream = torch.cuda.Stream(device=self._device_index)
+        mine = sum(((rank >> j) & 1) << i for i, j in enumerate(rank_bits))
+        sub = ntiles >> k
+        bits = np.ascontiguousarray(np.asarray(lbits, dtype=np.int32))
+        tag = self._tag(shard)
+        flag = self.__dict__.get("_barrier_flag")
+        if flag is None:
+            flag = self._barrier_flag = torch.zeros(1, dtype=torch.int32, device=self.torch_device)
+        for d in range(1, 1 << k):
+            a = mine ^ d
+            peer = rank
+            for i, j in enumerate(rank_bits):
+                peer = (peer & ~(1 << j)) | (((a >> i) & 1) << j)
+            _capi.check(self._lib.qj_program_run_tiles(h, handle, ptr, last, a * sub, sub))
+            done = torch.cuda.Event()
+            done.record(main)
+            with torch.cuda.stream(side):
+                side.wait_event(done)
+                comm.dist.all_reduce(flag, group=comm.group)       # every rank finished its sub-block of step d
+                _capi.check(self._lib.qj_set_stream(h, ctypes.c_void_p(side.cuda_stream)))
+                try:
+                    _capi.check(self._lib.qj_swap_bits_peer(h, ptr, ptrs[peer], tag, nlocal, bits.ctypes.data, k,
+                                                            a, mine, 0 if rank < peer else 1, 2))
+                finally:
+                    _capi.check(self._lib.qj_set_stream(h, ctypes.c_void_p(main.cuda_stream)))
+        _capi.check(self._lib.qj_program_run_tiles(h, handle, ptr, last, mine * sub, sub))   # the sub-block that stays
+        with torch.cuda.stream(side):
+            comm.dist.all_reduce(flag, group=comm.group)           # every swap everywhere is complete
+            fin = torch.cuda.Event()
+            fin.record(side)
+        main.wait_event(fin)
+        return shard, moved
+
     def shard_exchange(self, shard, nlocal, lbit, peer, is_upper, comm, chunk_bytes=1 << 29):
         """Global<->local qubit swap with rank `peer` (ops.swap_pieces semantics): the amplitudes
         of this shard whose local bit `lbit` equals (1 - is_upper) are exchanged with the peer's

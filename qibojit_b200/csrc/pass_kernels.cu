@@ -123,6 +123,7 @@ struct PassGeom {
     int io_fast;           // the launch geometry satisfies the conditions above
     int nrounds_smem;      // rounds whose per-thread constants are staged in shared memory
     int zero_input;        // the input is |0...0>: the launch does not read the state (state preparation fused in)
+    int64_t tile_begin, tile_end;   // the tiles this launch processes (all of them unless a caller pipelines sub-blocks)
 };
 
 // ---- program image (16-byte units) -------------------------------------------------------------
@@ -787,7 +788,7 @@ k_pass(Cx<T> *__restrict__ state, const __grid_constant__ PassGeom pg, const Cx<
     // this thread's part of every global vector address of the fast tile IO
     const int64_t io_thr = fast_io ? int64_t(lane_off) + s_runoff[run_t] : 0;
 
-    for (int64_t tile_id = blockIdx.x; tile_id < pg.ntiles; tile_id += gridDim.x) {
+    for (int64_t tile_id = pg.tile_begin + blockIdx.x; tile_id < pg.tile_end; tile_id += gridDim.x) {
         // tile base: insert zeros at the high local bits
         int64_t tb = tile_id;
 #pragma unroll 1
@@ -2271,8 +2272,12 @@ extern "C" int qj_program_stats(const qj_program *p, int64_t *nlaunches, int64_t
 
 namespace {
 template <typename T>
-int launch_pass(qj_handle *h, const qj_program *p, void *state, int li, int zero_input) {
+int launch_pass(qj_handle *h, const qj_program *p, void *state, int li, int zero_input, int64_t tile_begin = 0,
+                int64_t tile_count = -1) {
     const qj_program::Launch &L = p->launches[li];
+    if (tile_count < 0) tile_count = L.geom.ntiles - tile_begin;
+    QJ_REQUIRE(tile_begin >= 0 && tile_count >= 0 && tile_begin + tile_count <= L.geom.ntiles, "tile range out of bounds");
+    if (tile_count == 0) return QJ_OK;
     static bool configured[kMaxDevices] = {false};   // the attribute is per device, not per process
     if (!configured[h->device]) {
         QJ_CUDA_OK(cudaFuncSetAttribute(k_pass<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 << 10));
@@ -2284,9 +2289,11 @@ int launch_pass(qj_handle *h, const qj_program *p, void *state, int li, int zero
     const int threads = std::max(1, std::min(kThreads, (1 << (L.geom.T - VS)) >> kVecRegBits));
     const int by_smem = (int)std::max<size_t>(1, (size_t(224) << 10) / (L.smem + 1024));
     const int per_sm = std::max(1, std::min(by_smem, 512 / threads));
-    const unsigned grid = (unsigned)std::min<int64_t>(L.geom.ntiles, int64_t(h->sm_count) * per_sm);
+    const unsigned grid = (unsigned)std::min<int64_t>(tile_count, int64_t(h->sm_count) * per_sm);
     PassGeom geom = L.geom;
     geom.zero_input = zero_input;
+    geom.tile_begin = tile_begin;
+    geom.tile_end = tile_begin + tile_count;
     k_pass<T><<<grid, threads, L.smem, h->stream>>>(
         reinterpret_cast<Cx<T> *>(state), geom, reinterpret_cast<const Cx<T> *>(p->d_tables), p->images[li]);
     h->launches++;
@@ -2326,6 +2333,24 @@ extern "C" int qj_program_run_ex(qj_handle *h, const qj_program *p, void *state,
         return QJ_OK;
     }
     return run_launches(h, p, state, first_launch, nlaunches, flags);
+}
+
+extern "C" int qj_program_run_tiles(qj_handle *h, const qj_program *p, void *state, int launch, int64_t tile_begin,
+                                    int64_t tile_count) {
+    qj::DeviceGuard device_guard(h);
+    QJ_REQUIRE(h && p && state, "null argument");
+    QJ_REQUIRE(launch >= 0 && launch < (int)p->launches.size(), "launch index out of range");
+    return (p->dtype == QJ_C128) ? launch_pass<double>(h, p, state, launch, 0, tile_begin, tile_count)
+                                 : launch_pass<float>(h, p, state, launch, 0, tile_begin, tile_count);
+}
+
+extern "C" int qj_program_launch_geometry(const qj_program *p, int launch, int64_t *out) {
+    QJ_REQUIRE(p && out, "null argument");
+    QJ_REQUIRE(launch >= 0 && launch < (int)p->launches.size(), "launch index out of range");
+    const PassGeom &g = p->launches[launch].geom;
+    out[0] = g.T; out[1] = g.r; out[2] = g.nh; out[3] = g.ntiles;
+    for (int b = 0; b < kMaxHiBits; b++) out[4 + b] = (b < g.nh) ? g.hibit[b] : -1;
+    return QJ_OK;
 }
 
 extern "C" int qj_program_run_launch(qj_handle *h, const qj_program *p, void *state, int launch) {

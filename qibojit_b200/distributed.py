@@ -530,8 +530,25 @@ class DistributedState:
             if not self._fresh:
                 raise ValueError("plan was made for a different qubit map")
         self._fresh = False
-        for step in steps:
-            if isinstance(step, LocalSegment):
+        steps_list = list(steps)
+        skip = False
+        for pos, step in enumerate(steps_list):
+            if skip:
+                skip = False
+                continue
+            nxt = steps_list[pos + 1] if pos + 1 < len(steps_list) else None
+            if (isinstance(step, LocalSegment) and isinstance(nxt, (MultiExchange, Exchange))
+                    and hasattr(b, "run_segment_then_exchange")):
+                # the segment's last pass is pipelined against the exchange (peer-memory transport)
+                lbits = nxt.local_bits if isinstance(nxt, MultiExchange) else [nxt.local_bit]
+                rbits = nxt.rank_bits if isinstance(nxt, MultiExchange) else [nxt.rank_bit]
+                self.shard, moved = b.run_segment_then_exchange(self.shard, self.nlocal, step, lbits, rbits,
+                                                                self.rank, self.comm, self.swap_chunk_bytes)
+                self.stats["local_segments"] += 1
+                self.stats["exchanges"] += 1
+                self.stats["exchange_bytes"] += int(moved)
+                skip = True
+            elif isinstance(step, LocalSegment):
                 self.shard = b.run_local_segment(self.shard, self.nlocal, step)
                 self.stats["local_segments"] += 1
             elif isinstance(step, MultiExchange):

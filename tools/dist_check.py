@@ -108,6 +108,31 @@ def main():
         b.release_peer_mappings()
     b.set_dtype("complex128")
 
+    # ---- pipelined exchange: the last pass of a segment overlapped with the peer exchange, sub-block
+    # by sub-block, against the plain order (bit for bit) and the einsum reference
+    for dtype in ("complex128", "complex64"):
+        b.set_dtype(dtype)
+        n = 20
+        tol = 1e-5 if dtype == "complex64" else 1e-12
+        for name, circuit in (("qft", circuits.qft(n)), ("supremacy", circuits.supremacy(n, depth=6)),
+                              ("variational", circuits.variational(n))):
+            outs = {}
+            for mode in ("1", "0"):
+                os.environ["QJ_OVERLAP_EXCHANGE"] = mode
+                before = getattr(b, "overlapped_exchanges", 0)
+                ds = DistributedState(b, n, comm=Comm(), dtype=dtype)
+                ds.execute(circuit.queue)
+                outs[mode] = (ds.to_numpy_full(), getattr(b, "overlapped_exchanges", 0) - before)
+                b.release_peer_mappings()
+            os.environ["QJ_OVERLAP_EXCHANGE"] = "1"
+            same = bool(np.array_equal(outs["1"][0], outs["0"][0]))
+            err = float(np.abs(outs["1"][0] - _reference_state(circuit, dtype)).max())
+            good = same and err < tol and outs["1"][1] >= 1 and outs["0"][1] == 0
+            say(rank, f"pipelined exchange {dtype:10s} {name:12s}: engaged {outs['1'][1]}x, identical to the plain order: {same}, "
+                      f"max|err| vs reference {err:.2e} {'ok' if good else 'FAIL'}")
+            ok &= good
+    b.set_dtype("complex128")
+
     # ---- two devices from one process (rank 0 drives its own device and its neighbour's)
     if rank == 0 and torch.cuda.device_count() >= 2:
         n = 16
