@@ -45,11 +45,13 @@ class TimedBackend:
         return segment.compiled.run_timed(
             shard, lambda kind, frac, fn: self._timed(kind, 2.0 * self._nbytes * frac, fn))
 
-    def run_segment_then_exchange(self, shard, nlocal, segment, lbits, rank_bits, rank, comm, chunk_bytes=1 << 29):
+    def run_segment_then_exchange(self, shard, nlocal, segment, lbits, rank_bits, rank, comm, chunk_bytes=1 << 29,
+                                  spare=None, defer=False):
         """Timed steps: the backend's pipelined path (last pass overlapped with the exchange).  The
         breakdown step (`enabled`): segment, then exchange, each launch bracketed by events."""
         if not self.enabled:
-            return self._b.run_segment_then_exchange(shard, nlocal, segment, lbits, rank_bits, rank, comm, chunk_bytes)
+            return self._b.run_segment_then_exchange(shard, nlocal, segment, lbits, rank_bits, rank, comm,
+                                                     chunk_bytes, spare=spare, defer=defer)
         shard = self.run_local_segment(shard, nlocal, segment)
         if len(lbits) == 1:
             peer = rank ^ (1 << rank_bits[0])

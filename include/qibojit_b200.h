@@ -158,6 +158,18 @@ int qj_swap_bits_peer(qj_handle *h, void *local, void *peer, int dtype, int nloc
 int qj_ipc_export(const void *ptr, void *handle64, int64_t *offset);
 int qj_ipc_open(const void *handle64, void **base_out);
 int qj_ipc_close(void *base);
+/* Stream-ordered handshake with `npeers` peers over mapped 32-bit flag words (the device-side
+ * replacement of the host barrier between the reference's per-piece kernels and its piece swaps,
+ * gpu.py:1497-1507, for one process per GPU): in stream order, publish epochs[i] into
+ * remote_slots[i] (the peer's flag slot for this rank), then wait until local_flags[src_ranks[i]]
+ * reaches epochs[i].  Work enqueued before the call is complete and visible to a peer that has
+ * seen the epoch.  A peer that does not answer within `timeout_seconds` (<= 0: 30 s) fails the
+ * launch (surfaces as a CUDA error at the next synchronisation) instead of hanging the device.  */
+int qj_peer_handshake(qj_handle *h, void *local_flags, void *const *remote_slots, const int32_t *src_ranks,
+                      const uint32_t *epochs, int npeers, double timeout_seconds);
+/* Asynchronous copy on the handle's stream by the copy engines (no SM is used, so it runs under a
+ * pass kernel at full rate); either side may be a peer allocation mapped with qj_ipc_open.      */
+int qj_copy_async(qj_handle *h, void *dst, const void *src, int64_t bytes);
 /* Staged variant for transports without peer mapping (NCCL send/recv of chunks):
  * pack: gather the half of `local` that leaves (bit m == 1 - is_upper) for amplitudes
  * [chunk_begin, chunk_begin + chunk_len) of the half-shard into contiguous `buf`;
@@ -256,6 +268,11 @@ int qj_program_run_ex(qj_handle *h, const qj_program *p, void *state, int first_
  * tiles, the high tile bits' index bits (8 entries, -1 = unused)}.                             */
 int qj_program_run_tiles(qj_handle *h, const qj_program *p, void *state, int launch, int64_t tile_begin,
                          int64_t tile_count);
+/* The same launch reading the tiles from `state` and storing them at the same positions of `out`
+ * (another buffer of the same size): the pass that precedes a qubit exchange deposits the sub-block
+ * this rank keeps straight into the buffer the exchange fills.                                  */
+int qj_program_run_tiles_to(qj_handle *h, const qj_program *p, const void *state, void *out, int launch,
+                            int64_t tile_begin, int64_t tile_count);
 int qj_program_launch_geometry(const qj_program *p, int launch, int64_t *out);
 int qj_program_stats(const qj_program *p, int64_t *nlaunches, int64_t *nrounds, int64_t *nmops);
 int qj_program_destroy(qj_handle *h, qj_program *p);

@@ -49,6 +49,8 @@ SIGNATURES = {
     "qj_ipc_export": (_I, [_P, _P, _c.POINTER(_L)]),
     "qj_ipc_open": (_I, [_P, _c.POINTER(_P)]),
     "qj_ipc_close": (_I, [_P]),
+    "qj_peer_handshake": (_I, [_P, _P, _P, _P, _P, _I, _c.c_double]),
+    "qj_copy_async": (_I, [_P, _P, _P, _L]),
     "qj_swap_pack": (_I, [_P, _P, _P, _I, _I, _I, _I, _L, _L]),
     "qj_swap_unpack": (_I, [_P, _P, _P, _I, _I, _I, _I, _L, _L]),
     "qj_swap_pack_bits": (_I, [_P, _P, _P, _I, _I, _P, _I, _I, _L, _L]),
@@ -58,6 +60,7 @@ SIGNATURES = {
     "qj_program_run_launch": (_I, [_P, _P, _P, _I]),
     "qj_program_run_ex": (_I, [_P, _P, _P, _I, _I, _I]),
     "qj_program_run_tiles": (_I, [_P, _P, _P, _I, _L, _L]),
+    "qj_program_run_tiles_to": (_I, [_P, _P, _P, _P, _I, _L, _L]),
     "qj_program_launch_geometry": (_I, [_P, _I, _P]),
     "qj_program_stats": (_I, [_P, _c.POINTER(_L), _c.POINTER(_L), _c.POINTER(_L)]),
     "qj_program_destroy": (_I, [_P, _P]),

@@ -590,6 +590,14 @@ class B200Backend(_QiboBackend):
             return self.zero_state(nlocal, dtype=dtype)
         return torch.zeros(1 << nlocal, dtype=getattr(torch, str(dtype)), device=self.torch_device)
 
+    def shard_spare(self, shard):
+        """Another uninitialised buffer like `shard`, or None when the device has no room for it."""
+        torch = _torch()
+        try:
+            return torch.empty_like(shard)
+        except torch.OutOfMemoryError:
+            return None
+
     def shard_from(self, piece, dtype):
         """This rank's piece of a caller-supplied state (host array or tensor on any device) as a
         device shard of its own (the caller keeps its state, cpu.py:96-119 semantics of `cast`)."""
@@ -605,7 +613,9 @@ class B200Backend(_QiboBackend):
     def run_local_segment(self, shard, nlocal, segment):
         """Run the local gates between two exchanges: compiled once into multi-gate passes
         (``planner.Program``, cached on the segment), or gate by gate when programs are off."""
+        pending = self.__dict__.pop("_pending_exchange", None)
         if not getattr(self, "use_programs", True):
+            self._settle_exchange(pending)
             for gate in segment.gates:
                 shard = gate.apply(self, shard, nlocal)
             return shard
@@ -614,7 +624,76 @@ class B200Backend(_QiboBackend):
 
             segment.compiled = Program(self, segment.gates, nlocal,
                                        dtype=str(shard.dtype).replace("torch.", ""))
-        return segment.compiled.run(shard)
+        self._run_compiled(segment.compiled, shard, nlocal, pending)
+        return shard
+
+    # -- an exchange that is still landing in the shard (see run_segment_then_exchange, `defer`)
+    def _settle_exchange(self, pending):
+        """The launch stream waits for the whole exchange (every pull into this rank's shard and
+        every peer's pull out of its previous buffer)."""
+        if pending is not None:
+            _torch().cuda.current_stream(self._device_index).wait_event(pending["fin"])
+        return None
+
+    def _launch_geometry(self, handle, launch):
+        import ctypes
+
+        geom = (ctypes.c_int64 * 12)()
+        _capi.check(self._lib.qj_program_launch_geometry(handle, launch, geom))
+        return {"T": int(geom[0]), "r": int(geom[1]), "ntiles": int(geom[3]),
+                "hibits": [int(v) for v in geom[4:12] if v >= 0]}
+
+    def _splits_on_top_bits(self, handle, launch, nlocal, k):
+        """Tiles per sub-block if the launch's tiles never straddle the 2^k sub-blocks of the top k
+        index bits (then sub-block a is the tile range [a * sub, (a + 1) * sub)), else 0."""
+        g = self._launch_geometry(handle, launch)
+        top = range(nlocal - k, nlocal)
+        if any(b in g["hibits"] for b in top) or g["r"] > nlocal - k or g["ntiles"] % (1 << k):
+            return 0
+        return g["ntiles"] >> k
+
+    def _run_compiled(self, prog, shard, nlocal, pending=None, hold_last=False):
+        """Run a compiled segment on `shard` in place.  `pending`: an exchange still landing in
+        `shard` -- the first launch then runs sub-block by sub-block in arrival order (when its tiles
+        allow it), so the tail of the exchange hides under it; anything else waits for the exchange.
+        `hold_last`: leave out the last launch of the trailing program and return (handle, index)."""
+        import ctypes
+
+        prog._check_open()
+        if shard.numel() != (1 << prog.nqubits) or str(shard.dtype).replace("torch.", "") != prog.dtype:
+            raise ValueError("state does not match the program's qubit count / dtype")
+        torch = _torch()
+        h, ptr = self._handle(), shard.data_ptr()
+        if pending is not None and pending["ptr"] != ptr:
+            pending = self._settle_exchange(pending)
+        held = None
+        for si, seg in enumerate(prog.segments):
+            if seg[0] != "program":
+                pending = self._settle_exchange(pending)
+                seg[1].apply(self, shard, nlocal)
+                continue
+            nl = ctypes.c_int64()
+            _capi.check(self._lib.qj_program_stats(seg[1], ctypes.byref(nl), None, None))
+            first, stop = 0, int(nl.value)
+            if hold_last and si == len(prog.segments) - 1:
+                stop -= 1
+                held = (seg[1], stop)
+            if pending is not None and stop > 0:
+                k = pending["k"]
+                sub = self._splits_on_top_bits(seg[1], 0, nlocal, k)
+                if sub:
+                    main = torch.cuda.current_stream(self._device_index)
+                    _capi.check(self._lib.qj_program_run_tiles(h, seg[1], ptr, 0, pending["mine"] * sub, sub))
+                    for a in pending["order"]:
+                        main.wait_event(pending["arrived"][a])
+                        _capi.check(self._lib.qj_program_run_tiles(h, seg[1], ptr, 0, a * sub, sub))
+                    first = 1
+                    self.pipelined_arrivals = getattr(self, "pipelined_arrivals", 0) + 1
+            pending = self._settle_exchange(pending)
+            if stop > first:
+                _capi.check(self._lib.qj_program_run_ex(h, seg[1], ptr, first, stop - first, 0))
+        self._settle_exchange(pending)
+        return held
 
     def shard_scale(self, shard, nlocal, phase):
         ph = np.asarray(phase, dtype=self._np_dtype(shard)).reshape(1)
@@ -678,6 +757,7 @@ class B200Backend(_QiboBackend):
         for base in self.__dict__.pop("_ipc_opened", {}).values():
             self._lib.qj_ipc_close(ctypes.c_void_p(base))
         self.__dict__.pop("_peer_cache", None)
+        self.__dict__.pop("_handshake_ptrs", None)
 
     def _peer_enabled(self, shard, comm):
         import os
@@ -717,14 +797,53 @@ class B200Backend(_QiboBackend):
                                                     len(lbits), mine_val, peer_val, 0 if comm.rank < peer else 1, 2))
         self._stream_barrier(comm)
 
-    def run_segment_then_exchange(self, shard, nlocal, segment, lbits, rank_bits, rank, comm, chunk_bytes=1 << 29):
+    def _peer_flags(self, comm):
+        """(this rank's flag words, {rank: that rank's flag words as mapped here}) for
+        `qj_peer_handshake`; slot r of every array is written by rank r only."""
+        torch = _torch()
+        flags = self.__dict__.get("_handshake_flags")
+        if flags is None:
+            flags = self._handshake_flags = torch.zeros(64, dtype=torch.int32, device=self.torch_device)
+            self._handshake_epoch = {}
+            torch.cuda.synchronize(self._device_index)
+        ptrs = self.__dict__.get("_handshake_ptrs")
+        if ptrs is None:
+            ptrs = self._handshake_ptrs = self._peer_pointers(flags, comm)
+        return flags, ptrs
+
+    def _peer_handshake(self, comm, peers, timeout=30.0):
+        """Stream-ordered rendezvous with `peers` (ranks) on the handle's current stream: what each side
+        enqueued before it is complete and visible to the other before anything enqueued after it starts."""
+        import ctypes
+
+        flags, ptrs = self._peer_flags(comm)
+        n = len(peers)
+        slots = (ctypes.c_void_p * n)(*[ptrs[p] + 4 * comm.rank for p in peers])
+        src = (ctypes.c_int32 * n)(*peers)
+        epoch = self._handshake_epoch
+        for p in peers:
+            epoch[p] = (epoch.get(p, 0) + 1) & 0xFFFFFFFF
+        eps = (ctypes.c_uint32 * n)(*[epoch[p] for p in peers])
+        _capi.check(self._lib.qj_peer_handshake(self._handle(), ctypes.c_void_p(flags.data_ptr()), slots, src, eps,
+                                                n, ctypes.c_double(timeout)))
+
+    def run_segment_then_exchange(self, shard, nlocal, segment, lbits, rank_bits, rank, comm, chunk_bytes=1 << 29,
+                                  spare=None, defer=False):
         """A local segment followed by the exchange of `lbits` <-> `rank_bits`, with the LAST pass of
-        the segment pipelined against the exchange over peer memory: that pass runs sub-block by
-        sub-block (XOR order: at step d this rank finishes the sub-block it trades with the rank at
-        distance d, which finishes its counterpart at the same step), and the swap of step d runs on
-        a side stream while the pass works on the sub-block of step d + 1.  Falls back to "segment,
-        then exchange" whenever the geometry does not allow it (exchanged bits inside the pass's tile
-        or not the shard's top bits, NCCL transport, gate-by-gate execution).  Returns (shard, bytes sent)."""
+        the segment pipelined against the exchange.  With a `spare` buffer of the shard's size the
+        exchange is out of place and uses no SM: the last pass runs sub-block by sub-block (XOR
+        order: at step d this rank finishes the sub-block that belongs to the rank at distance d,
+        which finishes this rank's sub-block at the same step, `slices` pieces each); as soon as a
+        piece is complete on both sides (a stream-ordered handshake over mapped flag words) the copy
+        engines pull the peer's piece over NVLink into its final place in `spare` while the pass
+        works on the next piece; the sub-block that stays is written by the pass straight into
+        `spare`.  Returns (spare, bytes sent) -- the caller keeps `shard` as its next spare.
+        `defer`: the caller's next call is `run_local_segment` / `run_segment_then_exchange` on the
+        returned buffer -- the launch stream then does not wait for the exchange here; the first pass
+        of that next segment takes the sub-blocks in arrival order instead (`_run_compiled`).
+        Falls back to "segment, then in-place exchange" (returning `shard`) without a spare or
+        whenever the geometry does not allow it (exchanged bits inside the pass's tile or not the
+        shard's top bits, NCCL transport, gate-by-gate execution)."""
         import ctypes
         import os
 
@@ -742,9 +861,12 @@ class B200Backend(_QiboBackend):
                 self.shard_exchange_multi(out, nlocal, lbits, rank_bits, rank, comm, chunk_bytes)
             return out, moved
 
-        if (os.environ.get("QJ_OVERLAP_EXCHANGE", "1") == "0" or not getattr(self, "overlap_exchange", True)
+        if (spare is None or os.environ.get("QJ_OVERLAP_EXCHANGE", "1") == "0"
+                or not getattr(self, "overlap_exchange", True)
                 or not getattr(self, "use_programs", True) or not self._peer_enabled(shard, comm)):
             return plain()
+        if spare.dtype != shard.dtype or spare.numel() != shard.numel() or spare.data_ptr() == shard.data_ptr():
+            raise ValueError("spare must be another buffer of the shard's size and dtype")
         if segment.compiled is None:
             from ..planner import Program
 
@@ -756,58 +878,75 @@ class B200Backend(_QiboBackend):
         nl = ctypes.c_int64()
         _capi.check(self._lib.qj_program_stats(handle, ctypes.byref(nl), None, None))
         last = int(nl.value) - 1
-        geom = (ctypes.c_int64 * 12)()
-        _capi.check(self._lib.qj_program_launch_geometry(handle, last, geom))
-        ntiles, hibits = int(geom[3]), [int(v) for v in geom[4:12] if v >= 0]
-        if last < 0 or any(b in hibits for b in lbits) or int(geom[1]) > nlocal - k or ntiles % (1 << k):
+        if last < 0:
             return plain()
+        sub = self._splits_on_top_bits(handle, last, nlocal, k)     # tiles per sub-block
+        if not sub:
+            return plain()
+        # a sub-block goes piece by piece: a piece is a tile range AND must be one contiguous byte range
+        # (what the copy engine moves), i.e. the index bits right below the exchanged ones must lie
+        # outside the launch's tile as well
+        slices = 1
+        want = max(1, int(os.environ.get("QJ_OVERLAP_SLICES", "8")))
+        while slices * 2 <= want and self._splits_on_top_bits(handle, last, nlocal, k + slices.bit_length()):
+            slices *= 2
 
         self.overlapped_exchanges = getattr(self, "overlapped_exchanges", 0) + 1
         h = self._handle()
-        ptr = shard.data_ptr()
-        for seg in prog.segments[:-1]:
-            if seg[0] == "program":
-                _capi.check(self._lib.qj_program_run(h, seg[1], ptr))
-            else:
-                seg[1].apply(self, shard, nlocal)
-        if last > 0:
-            _capi.check(self._lib.qj_program_run_ex(h, handle, ptr, 0, last, 0))
-        ptrs = self._peer_pointers(shard, comm)
+        ptr, out = shard.data_ptr(), spare.data_ptr()
+        src_ptrs = self._peer_pointers(shard, comm)       # the peers' shards (the sources of the pulls)
+        self._peer_flags(comm)
+        # everything but the last launch (a previous exchange still landing in `shard` is taken in
+        # by the first one); this also orders the launch stream after every peer's pull out of
+        # `spare`, the buffer this exchange fills
+        self._run_compiled(prog, shard, nlocal, self.__dict__.pop("_pending_exchange", None), hold_last=True)
         main = torch.cuda.current_stream(self._device_index)
         side = self.__dict__.get("_side_stream")
         if side is None:
-            side = self._side_stream = torch.cuda.Stream(device=self._device_index)
+            side = self._side_stream = torch.cuda.Stream(device=self._device_index, priority=-1)
         mine = sum(((rank >> j) & 1) << i for i, j in enumerate(rank_bits))
-        sub = ntiles >> k
-        bits = np.ascontiguousarray(np.asarray(lbits, dtype=np.int32))
-        tag = self._tag(shard)
-        flag = self.__dict__.get("_barrier_flag")
-        if flag is None:
-            flag = self._barrier_flag = torch.zeros(1, dtype=torch.int32, device=self.torch_device)
+        piece = sub // slices
+        sub_bytes = (1 << (nlocal - k)) * esize
+        piece_bytes = sub_bytes // slices
+        side_ptr, main_ptr = ctypes.c_void_p(side.cuda_stream), ctypes.c_void_p(main.cuda_stream)
+        peers, order, arrived = [], [], {}
         for d in range(1, 1 << k):
             a = mine ^ d
             peer = rank
             for i, j in enumerate(rank_bits):
                 peer = (peer & ~(1 << j)) | (((a >> i) & 1) << j)
-            _capi.check(self._lib.qj_program_run_tiles(h, handle, ptr, last, a * sub, sub))
-            done = torch.cuda.Event()
-            done.record(main)
-            with torch.cuda.stream(side):
+            peers.append(peer)
+            for s in range(slices):
+                _capi.check(self._lib.qj_program_run_tiles(h, handle, ptr, last, a * sub + s * piece, piece))
+                done = torch.cuda.Event()
+                done.record(main)
                 side.wait_event(done)
-                comm.dist.all_reduce(flag, group=comm.group)       # every rank finished its sub-block of step d
-                _capi.check(self._lib.qj_set_stream(h, ctypes.c_void_p(side.cuda_stream)))
+                _capi.check(self._lib.qj_set_stream(h, side_ptr))
                 try:
-                    _capi.check(self._lib.qj_swap_bits_peer(h, ptr, ptrs[peer], tag, nlocal, bits.ctypes.data, k,
-                                                            a, mine, 0 if rank < peer else 1, 2))
+                    self._peer_handshake(comm, [peer])     # both sides finished piece s of what they trade
+                    off = s * piece_bytes
+                    _capi.check(self._lib.qj_copy_async(h, ctypes.c_void_p(out + a * sub_bytes + off),
+                                                        ctypes.c_void_p(src_ptrs[peer] + mine * sub_bytes + off),
+                                                        piece_bytes))
                 finally:
-                    _capi.check(self._lib.qj_set_stream(h, ctypes.c_void_p(main.cuda_stream)))
-        _capi.check(self._lib.qj_program_run_tiles(h, handle, ptr, last, mine * sub, sub))   # the sub-block that stays
-        with torch.cuda.stream(side):
-            comm.dist.all_reduce(flag, group=comm.group)           # every swap everywhere is complete
-            fin = torch.cuda.Event()
-            fin.record(side)
-        main.wait_event(fin)
-        return shard, moved
+                    _capi.check(self._lib.qj_set_stream(h, main_ptr))
+            order.append(a)
+            arrived[a] = torch.cuda.Event()
+            arrived[a].record(side)
+        # the sub-block that stays: from the shard straight into its place in the new buffer
+        _capi.check(self._lib.qj_program_run_tiles_to(h, handle, ptr, ctypes.c_void_p(out), last, mine * sub, sub))
+        _capi.check(self._lib.qj_set_stream(h, side_ptr))
+        try:
+            self._peer_handshake(comm, peers)              # every pull from this rank's shard is complete
+        finally:
+            _capi.check(self._lib.qj_set_stream(h, main_ptr))
+        fin = torch.cuda.Event()
+        fin.record(side)
+        if defer:
+            self._pending_exchange = {"k": k, "mine": mine, "order": order, "arrived": arrived, "fin": fin, "ptr": out}
+        else:
+            main.wait_event(fin)
+        return spare, moved
 
     def shard_exchange(self, shard, nlocal, lbit, peer, is_upper, comm, chunk_bytes=1 << 29):
         """Global<->local qubit swap with rank `peer` (ops.swap_pieces semantics): the amplitudes

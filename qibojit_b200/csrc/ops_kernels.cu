@@ -557,6 +557,39 @@ k_swap_bits_peer(float4 *__restrict__ local, float4 *__restrict__ peer, const __
     }
 }
 
+
+// Stream-ordered handshake with peers over mapped flag words (one 32-bit slot per writing rank in
+// every rank's flag array).  Thread i publishes epochs[i] into its peer's slot for this rank, then
+// waits until that peer's epoch shows up in this rank's own array.  Everything enqueued before the
+// kernel on this stream is complete (stream order) and fenced before the flag is published, so a
+// peer that has seen the epoch may read this rank's memory; a peer that never shows up trips the
+// timeout and the launch fails instead of hanging the device.
+struct PeerFlags {
+    unsigned *remote_slot[64];
+    int src_rank[64];
+    unsigned epoch[64];
+    int n;
+};
+__global__ void k_peer_handshake(volatile unsigned *local_flags, const __grid_constant__ PeerFlags pf,
+                                 unsigned long long timeout_ns) {
+    const int i = threadIdx.x;
+    if (i >= pf.n) return;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pf.remote_slot[i]), "r"(pf.epoch[i]) : "memory");
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        unsigned seen;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(local_flags + pf.src_rank[i]) : "memory");
+        if (int(seen - pf.epoch[i]) >= 0) break;
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (t - t0 > timeout_ns) __trap();
+        __nanosleep(200);
+    }
+    __threadfence_system();
+}
+
 template <typename F>
 int launch_checked(qj_handle *h, F &&f) {
     f();
@@ -1010,6 +1043,34 @@ extern "C" int qj_ipc_open(const void *handle64, void **base_out) {
 }
 extern "C" int qj_ipc_close(void *base) {
     if (base) QJ_CUDA_OK(cudaIpcCloseMemHandle(base));
+    return QJ_OK;
+}
+
+extern "C" int qj_peer_handshake(qj_handle *h, void *local_flags, void *const *remote_slots, const int32_t *src_ranks,
+                                 const uint32_t *epochs, int npeers, double timeout_seconds) {
+    qj::DeviceGuard device_guard(h);
+    QJ_REQUIRE(h && local_flags && remote_slots && src_ranks && epochs, "null argument");
+    QJ_REQUIRE(npeers >= 1 && npeers <= 64, "between 1 and 64 peers per handshake");
+    PeerFlags pf;
+    pf.n = npeers;
+    for (int i = 0; i < npeers; i++) {
+        QJ_REQUIRE(remote_slots[i] != nullptr && src_ranks[i] >= 0 && src_ranks[i] < 64, "bad peer slot");
+        pf.remote_slot[i] = reinterpret_cast<unsigned *>(remote_slots[i]);
+        pf.src_rank[i] = src_ranks[i];
+        pf.epoch[i] = epochs[i];
+    }
+    const unsigned long long ns = (unsigned long long)(1e9 * (timeout_seconds > 0 ? timeout_seconds : 30.0));
+    return launch_checked(h, [&] {
+        k_peer_handshake<<<1, 64, 0, h->stream>>>(reinterpret_cast<volatile unsigned *>(local_flags), pf, ns);
+    });
+}
+
+extern "C" int qj_copy_async(qj_handle *h, void *dst, const void *src, int64_t bytes) {
+    qj::DeviceGuard device_guard(h);
+    QJ_REQUIRE(h && dst && src && bytes >= 0, "bad argument");
+    if (bytes == 0) return QJ_OK;
+    // (copy engine; either side may be a peer allocation mapped with qj_ipc_open)
+    QJ_CUDA_OK(cudaMemcpyAsync(dst, src, size_t(bytes), cudaMemcpyDefault, h->stream));
     return QJ_OK;
 }
 

@@ -124,6 +124,7 @@ struct PassGeom {
     int nrounds_smem;      // rounds whose per-thread constants are staged in shared memory
     int zero_input;        // the input is |0...0>: the launch does not read the state (state preparation fused in)
     int64_t tile_begin, tile_end;   // the tiles this launch processes (all of them unless a caller pipelines sub-blocks)
+    int64_t out_off;                // where the tiles are stored, in 16-byte vectors from the state pointer (0: in place)
 };
 
 // ---- program image (16-byte units) -------------------------------------------------------------
@@ -1129,7 +1130,7 @@ k_pass(Cx<T> *__restrict__ state, const __grid_constant__ PassGeom pg, const Cx<
 
         // ---- store the tile (four vectors in flight per thread)
         if (fast_io) {
-            uint4 *const gdst = gvec + base_vec + io_thr;
+            uint4 *const gdst = gvec + pg.out_off + base_vec + io_thr;
 #pragma unroll
             for (int u0 = 0; u0 < 16; u0 += 4) {
                 uint4 q[4];
@@ -1150,7 +1151,7 @@ k_pass(Cx<T> *__restrict__ state, const __grid_constant__ PassGeom pg, const Cx<
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
                     const int lv = v0 + u * nthr;
-                    if (lv < nvec) gvec[base_vec + s_runoff[lv >> rv] + (lv & rvmask)] = q[u];
+                    if (lv < nvec) gvec[pg.out_off + base_vec + s_runoff[lv >> rv] + (lv & rvmask)] = q[u];
                 }
             }
         }
@@ -2273,7 +2274,7 @@ extern "C" int qj_program_stats(const qj_program *p, int64_t *nlaunches, int64_t
 namespace {
 template <typename T>
 int launch_pass(qj_handle *h, const qj_program *p, void *state, int li, int zero_input, int64_t tile_begin = 0,
-                int64_t tile_count = -1) {
+                int64_t tile_count = -1, void *out = nullptr, bool leave_a_slot = false) {
     const qj_program::Launch &L = p->launches[li];
     if (tile_count < 0) tile_count = L.geom.ntiles - tile_begin;
     QJ_REQUIRE(tile_begin >= 0 && tile_count >= 0 && tile_begin + tile_count <= L.geom.ntiles, "tile range out of bounds");
@@ -2289,11 +2290,18 @@ int launch_pass(qj_handle *h, const qj_program *p, void *state, int li, int zero
     const int threads = std::max(1, std::min(kThreads, (1 << (L.geom.T - VS)) >> kVecRegBits));
     const int by_smem = (int)std::max<size_t>(1, (size_t(224) << 10) / (L.smem + 1024));
     const int per_sm = std::max(1, std::min(by_smem, 512 / threads));
-    const unsigned grid = (unsigned)std::min<int64_t>(tile_count, int64_t(h->sm_count) * per_sm);
+    // The CTAs of a launch live until its last tile (grid-stride loop) and two or four of them hold
+    // every register of an SM.  A pipelined sub-block launch therefore starts one CTA short of the
+    // device's capacity: the free slot is where the high-priority handshake kernel of the exchange
+    // runs while the pass is in flight (with a full grid it would wait for the launch to drain).
+    const int64_t slots = int64_t(h->sm_count) * per_sm - (leave_a_slot ? 1 : 0);
+    const unsigned grid = (unsigned)std::min<int64_t>(tile_count, std::max<int64_t>(1, slots));
     PassGeom geom = L.geom;
     geom.zero_input = zero_input;
     geom.tile_begin = tile_begin;
     geom.tile_end = tile_begin + tile_count;
+    // (a byte difference of two 16-byte aligned device addresses; applied to the vector pointer in the kernel)
+    geom.out_off = out ? (reinterpret_cast<intptr_t>(out) - reinterpret_cast<intptr_t>(state)) / 16 : 0;
     k_pass<T><<<grid, threads, L.smem, h->stream>>>(
         reinterpret_cast<Cx<T> *>(state), geom, reinterpret_cast<const Cx<T> *>(p->d_tables), p->images[li]);
     h->launches++;
@@ -2340,8 +2348,20 @@ extern "C" int qj_program_run_tiles(qj_handle *h, const qj_program *p, void *sta
     qj::DeviceGuard device_guard(h);
     QJ_REQUIRE(h && p && state, "null argument");
     QJ_REQUIRE(launch >= 0 && launch < (int)p->launches.size(), "launch index out of range");
-    return (p->dtype == QJ_C128) ? launch_pass<double>(h, p, state, launch, 0, tile_begin, tile_count)
-                                 : launch_pass<float>(h, p, state, launch, 0, tile_begin, tile_count);
+    return (p->dtype == QJ_C128) ? launch_pass<double>(h, p, state, launch, 0, tile_begin, tile_count, nullptr, true)
+                                 : launch_pass<float>(h, p, state, launch, 0, tile_begin, tile_count, nullptr, true);
+}
+
+extern "C" int qj_program_run_tiles_to(qj_handle *h, const qj_program *p, const void *state, void *out, int launch,
+                                       int64_t tile_begin, int64_t tile_count) {
+    qj::DeviceGuard device_guard(h);
+    QJ_REQUIRE(h && p && state && out, "null argument");
+    QJ_REQUIRE(((reinterpret_cast<uintptr_t>(state) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
+               "state and out must be 16-byte aligned");
+    QJ_REQUIRE(launch >= 0 && launch < (int)p->launches.size(), "launch index out of range");
+    void *src = const_cast<void *>(state);
+    return (p->dtype == QJ_C128) ? launch_pass<double>(h, p, src, launch, 0, tile_begin, tile_count, out, true)
+                                 : launch_pass<float>(h, p, src, launch, 0, tile_begin, tile_count, out, true);
 }
 
 extern "C" int qj_program_launch_geometry(const qj_program *p, int launch, int64_t *out) {

@@ -180,6 +180,10 @@ class DistributedState:
                       "skipped": 0, "relabelled_swaps": 0}
         self._fresh = True   # still |0...0>: the qubit map may be chosen freely
         self.relabel_swaps = True
+        # second shard-sized buffer of the out-of-place, copy-engine exchange (allocated on first use
+        # when every rank has the room; None + _spare_tried: the in-place exchange is used)
+        self._spare = None
+        self._spare_tried = False
         if initial_state is None:
             self.shard = backend.shard_zeros(self.nlocal, self.dtype, one_at_zero=(self.rank == 0))
         else:
@@ -520,6 +524,27 @@ class DistributedState:
         steps.final_map = list(self.bit_of)
         return steps
 
+    def spare_buffer(self):
+        """The second shard-sized buffer that lets an exchange run out of place under the last pass
+        (`run_segment_then_exchange`), or None: allocated once, only if EVERY rank has the memory
+        (ranks must agree on the exchange protocol) and the backend can use it."""
+        import os
+
+        if self._spare is not None or self._spare_tried:
+            return self._spare
+        self._spare_tried = True
+        b = self.backend
+        if (self.comm.world == 1 or not hasattr(b, "shard_spare") or os.environ.get("QJ_OVERLAP_EXCHANGE", "1") == "0"
+                or os.environ.get("QJ_PEER_EXCHANGE", "1") == "0"):
+            return None
+        spare = b.shard_spare(self.shard)
+        import torch
+
+        ok = torch.tensor([0.0 if spare is None else 1.0], dtype=torch.float64, device=self.shard.device)
+        self.comm.dist.all_reduce(ok, op=self.comm.dist.ReduceOp.MIN, group=self.comm.group)
+        self._spare = spare if float(ok[0]) > 0 else None
+        return self._spare
+
     def run(self, steps):
         """Execute planned steps on the shard (local segments are compiled into multi-gate pass
         programs by the backend the first time they run, and cached on the step)."""
@@ -542,8 +567,15 @@ class DistributedState:
                 # the segment's last pass is pipelined against the exchange (peer-memory transport)
                 lbits = nxt.local_bits if isinstance(nxt, MultiExchange) else [nxt.local_bit]
                 rbits = nxt.rank_bits if isinstance(nxt, MultiExchange) else [nxt.rank_bit]
+                before = self.shard
+                after = steps_list[pos + 2] if pos + 2 < len(steps_list) else None
+                # (another segment follows: its first pass takes the sub-blocks as they arrive)
                 self.shard, moved = b.run_segment_then_exchange(self.shard, self.nlocal, step, lbits, rbits,
-                                                                self.rank, self.comm, self.swap_chunk_bytes)
+                                                                self.rank, self.comm, self.swap_chunk_bytes,
+                                                                spare=self.spare_buffer(),
+                                                                defer=isinstance(after, LocalSegment))
+                if self.shard is not before:      # exchanged out of place: the old shard is the next spare
+                    self._spare = before
                 self.stats["local_segments"] += 1
                 self.stats["exchanges"] += 1
                 self.stats["exchange_bytes"] += int(moved)
