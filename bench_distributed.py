@@ -46,12 +46,12 @@ class TimedBackend:
             shard, lambda kind, frac, fn: self._timed(kind, 2.0 * self._nbytes * frac, fn))
 
     def run_segment_then_exchange(self, shard, nlocal, segment, lbits, rank_bits, rank, comm, chunk_bytes=1 << 29,
-                                  spare=None, defer=False):
+                                  spare=None):
         """Timed steps: the backend's pipelined path (last pass overlapped with the exchange).  The
         breakdown step (`enabled`): segment, then exchange, each launch bracketed by events."""
         if not self.enabled:
             return self._b.run_segment_then_exchange(shard, nlocal, segment, lbits, rank_bits, rank, comm,
-                                                     chunk_bytes, spare=spare, defer=defer)
+                                                     chunk_bytes, spare=spare)
         shard = self.run_local_segment(shard, nlocal, segment)
         if len(lbits) == 1:
             peer = rank ^ (1 << rank_bits[0])
@@ -175,6 +175,7 @@ def time_sharded(backend, workload, nqubits, dtype, steps, warmup, world, rank, 
     torch.cuda.synchronize()
     dist.barrier()
     launches0 = backend.launch_count()
+    pipelined0 = getattr(backend, "overlapped_exchanges", 0)
     for k in state.stats:
         state.stats[k] = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -191,6 +192,7 @@ def time_sharded(backend, workload, nqubits, dtype, steps, warmup, world, rank, 
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_per_step = float(ms[0]) / steps
     launches = backend.launch_count() - launches0
+    pipelined = getattr(backend, "overlapped_exchanges", 0) - pipelined0
     stats = dict(state.stats)
     # per-kernel breakdown from two extra steps with every launch and exchange bracketed by events
     # (not pipelined: the timed steps above overlap the last pass of a segment with the exchange)
@@ -228,8 +230,11 @@ def time_sharded(backend, workload, nqubits, dtype, steps, warmup, world, rank, 
         "plan_ms": plan_ms, "local_segments": sum(isinstance(st, LocalSegment) for st in steps_plan),
         "shard_bytes": amp << nlocal, "exchanges_per_step": stats["exchanges"] / steps,
         "exchange_bytes_per_rank_per_step": stats["exchange_bytes"] / steps,
-        "exchange_transport": "peer memory (CUDA IPC over NVLink, in-place swap kernel)"
+        "exchange_transport": ("peer memory (CUDA IPC over NVLink): copy-engine pulls into a second shard buffer, "
+                               "pipelined under the last pass of the segment" if pipelined else
+                               "peer memory (CUDA IPC over NVLink, in-place swap kernel)")
                               if getattr(backend, "_peer_cache", None) else "NCCL send/recv through staging buffers",
+        "pipelined_exchanges_per_step": pipelined / steps,
         "gpu_launches": int(launches), "program_upload_bytes": int(h2d),
         "roofline": {"bound": "hbm", "kernel": "k_pass (multi-gate tile pass, 2*shard bytes per launch)" if dom == "pass" else dom,
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,

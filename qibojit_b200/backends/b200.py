@@ -613,9 +613,7 @@ class B200Backend(_QiboBackend):
     def run_local_segment(self, shard, nlocal, segment):
         """Run the local gates between two exchanges: compiled once into multi-gate passes
         (``planner.Program``, cached on the segment), or gate by gate when programs are off."""
-        pending = self.__dict__.pop("_pending_exchange", None)
         if not getattr(self, "use_programs", True):
-            self._settle_exchange(pending)
             for gate in segment.gates:
                 shard = gate.apply(self, shard, nlocal)
             return shard
@@ -624,16 +622,7 @@ class B200Backend(_QiboBackend):
 
             segment.compiled = Program(self, segment.gates, nlocal,
                                        dtype=str(shard.dtype).replace("torch.", ""))
-        self._run_compiled(segment.compiled, shard, nlocal, pending)
-        return shard
-
-    # -- an exchange that is still landing in the shard (see run_segment_then_exchange, `defer`)
-    def _settle_exchange(self, pending):
-        """The launch stream waits for the whole exchange (every pull into this rank's shard and
-        every peer's pull out of its previous buffer)."""
-        if pending is not None:
-            _torch().cuda.current_stream(self._device_index).wait_event(pending["fin"])
-        return None
+        return segment.compiled.run(shard)
 
     def _launch_geometry(self, handle, launch):
         import ctypes
@@ -643,57 +632,19 @@ class B200Backend(_QiboBackend):
         return {"T": int(geom[0]), "r": int(geom[1]), "ntiles": int(geom[3]),
                 "hibits": [int(v) for v in geom[4:12] if v >= 0]}
 
-    def _splits_on_top_bits(self, handle, launch, nlocal, k):
-        """Tiles per sub-block if the launch's tiles never straddle the 2^k sub-blocks of the top k
-        index bits (then sub-block a is the tile range [a * sub, (a + 1) * sub)), else 0."""
-        g = self._launch_geometry(handle, launch)
-        top = range(nlocal - k, nlocal)
-        if any(b in g["hibits"] for b in top) or g["r"] > nlocal - k or g["ntiles"] % (1 << k):
-            return 0
-        return g["ntiles"] >> k
-
-    def _run_compiled(self, prog, shard, nlocal, pending=None, hold_last=False):
-        """Run a compiled segment on `shard` in place.  `pending`: an exchange still landing in
-        `shard` -- the first launch then runs sub-block by sub-block in arrival order (when its tiles
-        allow it), so the tail of the exchange hides under it; anything else waits for the exchange.
-        `hold_last`: leave out the last launch of the trailing program and return (handle, index)."""
-        import ctypes
-
-        prog._check_open()
-        if shard.numel() != (1 << prog.nqubits) or str(shard.dtype).replace("torch.", "") != prog.dtype:
-            raise ValueError("state does not match the program's qubit count / dtype")
-        torch = _torch()
-        h, ptr = self._handle(), shard.data_ptr()
-        if pending is not None and pending["ptr"] != ptr:
-            pending = self._settle_exchange(pending)
-        held = None
-        for si, seg in enumerate(prog.segments):
-            if seg[0] != "program":
-                pending = self._settle_exchange(pending)
-                seg[1].apply(self, shard, nlocal)
-                continue
-            nl = ctypes.c_int64()
-            _capi.check(self._lib.qj_program_stats(seg[1], ctypes.byref(nl), None, None))
-            first, stop = 0, int(nl.value)
-            if hold_last and si == len(prog.segments) - 1:
-                stop -= 1
-                held = (seg[1], stop)
-            if pending is not None and stop > 0:
-                k = pending["k"]
-                sub = self._splits_on_top_bits(seg[1], 0, nlocal, k)
-                if sub:
-                    main = torch.cuda.current_stream(self._device_index)
-                    _capi.check(self._lib.qj_program_run_tiles(h, seg[1], ptr, 0, pending["mine"] * sub, sub))
-                    for a in pending["order"]:
-                        main.wait_event(pending["arrived"][a])
-                        _capi.check(self._lib.qj_program_run_tiles(h, seg[1], ptr, 0, a * sub, sub))
-                    first = 1
-                    self.pipelined_arrivals = getattr(self, "pipelined_arrivals", 0) + 1
-            pending = self._settle_exchange(pending)
-            if stop > first:
-                _capi.check(self._lib.qj_program_run_ex(h, seg[1], ptr, first, stop - first, 0))
-        self._settle_exchange(pending)
-        return held
+    @staticmethod
+    def _tile_split(geom, nlocal, ntop):
+        """How a launch's tiles split over the top `ntop` index bits: (free, tiles per block) where
+        `free` are the positions (0 = lowest of the ntop bits) of the top bits OUTSIDE the tile -- the
+        tiles whose number has the value v in its top len(free) bits are exactly the amplitudes whose
+        free bits spell v, the tile range [v * per, (v + 1) * per) -- or None if the contiguous part of
+        the tile reaches into the top bits."""
+        if geom["r"] > nlocal - ntop:
+            return None
+        free = [i for i in range(ntop) if (nlocal - ntop + i) not in geom["hibits"]]
+        if geom["ntiles"] % (1 << len(free)):
+            return None
+        return free, geom["ntiles"] >> len(free)
 
     def shard_scale(self, shard, nlocal, phase):
         ph = np.asarray(phase, dtype=self._np_dtype(shard)).reshape(1)
@@ -828,22 +779,21 @@ class B200Backend(_QiboBackend):
                                                 n, ctypes.c_double(timeout)))
 
     def run_segment_then_exchange(self, shard, nlocal, segment, lbits, rank_bits, rank, comm, chunk_bytes=1 << 29,
-                                  spare=None, defer=False):
+                                  spare=None):
         """A local segment followed by the exchange of `lbits` <-> `rank_bits`, with the LAST pass of
         the segment pipelined against the exchange.  With a `spare` buffer of the shard's size the
-        exchange is out of place and uses no SM: the last pass runs sub-block by sub-block (XOR
-        order: at step d this rank finishes the sub-block that belongs to the rank at distance d,
-        which finishes this rank's sub-block at the same step, `slices` pieces each); as soon as a
-        piece is complete on both sides (a stream-ordered handshake over mapped flag words) the copy
-        engines pull the peer's piece over NVLink into its final place in `spare` while the pass
-        works on the next piece; the sub-block that stays is written by the pass straight into
-        `spare`.  Returns (spare, bytes sent) -- the caller keeps `shard` as its next spare.
-        `defer`: the caller's next call is `run_local_segment` / `run_segment_then_exchange` on the
-        returned buffer -- the launch stream then does not wait for the exchange here; the first pass
-        of that next segment takes the sub-blocks in arrival order instead (`_run_compiled`).
+        exchange is out of place and uses no SM: the last pass runs block by block over the exchanged
+        bits its tiles do not contain (XOR order: at step d this rank finishes the block that holds
+        the sub-blocks of the ranks at distance d, which finish the block holding this rank's
+        sub-block at the same step); as soon as a block is complete on both sides (a stream-ordered
+        handshake over mapped flag words) the copy engines pull this rank's sub-blocks out of the
+        peers' shards over NVLink into their final place in `spare`, while the pass works on the next
+        block.  The sub-block that stays is written by the pass straight into `spare` (or copied, when
+        its block also holds peers' sub-blocks).  Returns (spare, bytes sent): the caller keeps
+        `shard` as its next spare.
         Falls back to "segment, then in-place exchange" (returning `shard`) without a spare or
-        whenever the geometry does not allow it (exchanged bits inside the pass's tile or not the
-        shard's top bits, NCCL transport, gate-by-gate execution)."""
+        whenever the geometry does not allow it (exchanged bits not the shard's top bits, NCCL
+        transport, gate-by-gate execution)."""
         import ctypes
         import os
 
@@ -872,80 +822,128 @@ class B200Backend(_QiboBackend):
 
             segment.compiled = Program(self, segment.gates, nlocal, dtype=str(shard.dtype).replace("torch.", ""))
         prog = segment.compiled
-        if not prog.segments or prog.segments[-1][0] != "program" or list(lbits) != list(range(nlocal - k, nlocal)):
+        # what THIS rank's program allows: (eligible, exchanged bits outside the last launch's tile,
+        # pieces per sub-block).  Ranks compile their own programs (gates controlled on global qubits
+        # differ), so the protocol is fixed by agreement: identical bit sets everywhere, the coarsest
+        # slicing, or the plain order on every rank.
+        handle, last, geom, free, slices = None, -1, None, [], 1
+        eligible = bool(prog.segments) and prog.segments[-1][0] == "program" and \
+            list(lbits) == list(range(nlocal - k, nlocal))
+        if eligible:
+            handle = prog.segments[-1][1]
+            nl = ctypes.c_int64()
+            _capi.check(self._lib.qj_program_stats(handle, ctypes.byref(nl), None, None))
+            last = int(nl.value) - 1
+            eligible = last >= 0
+        if eligible:
+            geom = self._launch_geometry(handle, last)
+            split = self._tile_split(geom, nlocal, k)
+            eligible = split is not None
+        if eligible:
+            free = split[0]                     # exchanged bits outside the tile (positions in lbits)
+            # a block goes piece by piece when it is a single sub-block: a piece is a tile range AND
+            # must be one contiguous byte range (what the copy engine moves), i.e. the index bits right
+            # below the exchanged ones must lie outside the launch's tile as well
+            want = max(1, int(os.environ.get("QJ_OVERLAP_SLICES", "8")))
+            while len(free) == k and slices * 2 <= want:
+                finer = self._tile_split(geom, nlocal, k + slices.bit_length())
+                if finer is None or len(finer[0]) != k + slices.bit_length():
+                    break
+                slices *= 2
+        agreed = getattr(segment, "_overlap_agreed", None)
+        agreed = agreed[1] if agreed is not None and agreed[0] is prog else None     # (per compiled program)
+        if agreed is None:
+            mask = sum(1 << i for i in free)
+            mine_desc = [int(eligible), -int(eligible), mask, -mask, slices]
+            t = torch.tensor(mine_desc, dtype=torch.int64, device=self.torch_device)
+            comm.dist.all_reduce(t, op=comm.dist.ReduceOp.MIN, group=comm.group)
+            lo_e, hi_e, lo_m, hi_m, min_slices = [int(v) for v in t.cpu().tolist()]
+            agreed = (lo_e == 1 and -hi_e == 1 and lo_m == -hi_m, int(min_slices))
+            segment._overlap_agreed = (prog, agreed)
+        if not agreed[0]:
             return plain()
-        handle = prog.segments[-1][1]
-        nl = ctypes.c_int64()
-        _capi.check(self._lib.qj_program_stats(handle, ctypes.byref(nl), None, None))
-        last = int(nl.value) - 1
-        if last < 0:
-            return plain()
-        sub = self._splits_on_top_bits(handle, last, nlocal, k)     # tiles per sub-block
-        if not sub:
-            return plain()
-        # a sub-block goes piece by piece: a piece is a tile range AND must be one contiguous byte range
-        # (what the copy engine moves), i.e. the index bits right below the exchanged ones must lie
-        # outside the launch's tile as well
-        slices = 1
-        want = max(1, int(os.environ.get("QJ_OVERLAP_SLICES", "8")))
-        while slices * 2 <= want and self._splits_on_top_bits(handle, last, nlocal, k + slices.bit_length()):
-            slices *= 2
+        slices = agreed[1]
+        nfree = len(free)
+        per_block = geom["ntiles"] >> nfree
+        inside = [i for i in range(k) if i not in free]
 
         self.overlapped_exchanges = getattr(self, "overlapped_exchanges", 0) + 1
+        self.overlapped_inside_tile = getattr(self, "overlapped_inside_tile", 0) + (1 if inside else 0)
         h = self._handle()
         ptr, out = shard.data_ptr(), spare.data_ptr()
         src_ptrs = self._peer_pointers(shard, comm)       # the peers' shards (the sources of the pulls)
         self._peer_flags(comm)
-        # everything but the last launch (a previous exchange still landing in `shard` is taken in
-        # by the first one); this also orders the launch stream after every peer's pull out of
-        # `spare`, the buffer this exchange fills
-        self._run_compiled(prog, shard, nlocal, self.__dict__.pop("_pending_exchange", None), hold_last=True)
+        # everything but the last launch
+        for seg in prog.segments[:-1]:
+            if seg[0] == "program":
+                _capi.check(self._lib.qj_program_run(h, seg[1], ptr))
+            else:
+                seg[1].apply(self, shard, nlocal)
+        if last > 0:
+            _capi.check(self._lib.qj_program_run_ex(h, handle, ptr, 0, last, 0))
         main = torch.cuda.current_stream(self._device_index)
         side = self.__dict__.get("_side_stream")
         if side is None:
             side = self._side_stream = torch.cuda.Stream(device=self._device_index, priority=-1)
-        mine = sum(((rank >> j) & 1) << i for i, j in enumerate(rank_bits))
-        piece = sub // slices
-        sub_bytes = (1 << (nlocal - k)) * esize
-        piece_bytes = sub_bytes // slices
         side_ptr, main_ptr = ctypes.c_void_p(side.cuda_stream), ctypes.c_void_p(main.cuda_stream)
-        peers, order, arrived = [], [], {}
-        for d in range(1, 1 << k):
-            a = mine ^ d
-            peer = rank
+        mine = sum(((rank >> j) & 1) << i for i, j in enumerate(rank_bits))
+        sub_bytes = (1 << (nlocal - k)) * esize
+
+        def rank_of(a):
+            r = rank
             for i, j in enumerate(rank_bits):
-                peer = (peer & ~(1 << j)) | (((a >> i) & 1) << j)
-            peers.append(peer)
+                r = (r & ~(1 << j)) | (((a >> i) & 1) << j)
+            return r
+
+        def block_of(a):                                   # a sub-block's block: its free bits, packed
+            return sum(((a >> i) & 1) << j for j, i in enumerate(free))
+
+        def on_side(fn):
+            _capi.check(self._lib.qj_set_stream(h, side_ptr))
+            try:
+                fn()
+            finally:
+                _capi.check(self._lib.qj_set_stream(h, main_ptr))
+
+        def after_main():
+            done = torch.cuda.Event()
+            done.record(main)
+            side.wait_event(done)
+
+        def pull(a, off, nbytes):
+            _capi.check(self._lib.qj_copy_async(h, ctypes.c_void_p(out + a * sub_bytes + off),
+                                                ctypes.c_void_p(src_ptrs[rank_of(a)] + mine * sub_bytes + off), nbytes))
+
+        my_block = block_of(mine)
+        everyone = []
+        for d in list(range(1, 1 << nfree)) + [0]:
+            block = my_block ^ d
+            partners = [a for a in range(1 << k) if block_of(a) == block and a != mine]
+            everyone += partners
+            if not partners:
+                # the block is this rank's own sub-block: from the shard straight into the new buffer
+                _capi.check(self._lib.qj_program_run_tiles_to(h, handle, ptr, ctypes.c_void_p(out), last,
+                                                              block * per_block, per_block))
+                continue
+            piece = per_block // slices
             for s in range(slices):
-                _capi.check(self._lib.qj_program_run_tiles(h, handle, ptr, last, a * sub + s * piece, piece))
-                done = torch.cuda.Event()
-                done.record(main)
-                side.wait_event(done)
-                _capi.check(self._lib.qj_set_stream(h, side_ptr))
-                try:
-                    self._peer_handshake(comm, [peer])     # both sides finished piece s of what they trade
-                    off = s * piece_bytes
-                    _capi.check(self._lib.qj_copy_async(h, ctypes.c_void_p(out + a * sub_bytes + off),
-                                                        ctypes.c_void_p(src_ptrs[peer] + mine * sub_bytes + off),
-                                                        piece_bytes))
-                finally:
-                    _capi.check(self._lib.qj_set_stream(h, main_ptr))
-            order.append(a)
-            arrived[a] = torch.cuda.Event()
-            arrived[a].record(side)
-        # the sub-block that stays: from the shard straight into its place in the new buffer
-        _capi.check(self._lib.qj_program_run_tiles_to(h, handle, ptr, ctypes.c_void_p(out), last, mine * sub, sub))
-        _capi.check(self._lib.qj_set_stream(h, side_ptr))
-        try:
-            self._peer_handshake(comm, peers)              # every pull from this rank's shard is complete
-        finally:
-            _capi.check(self._lib.qj_set_stream(h, main_ptr))
+                _capi.check(self._lib.qj_program_run_tiles(h, handle, ptr, last, block * per_block + s * piece, piece))
+                after_main()
+
+                def step(s=s):
+                    # both sides finished this piece of what they trade
+                    self._peer_handshake(comm, [rank_of(a) for a in partners])
+                    for a in partners:
+                        pull(a, s * (sub_bytes // slices), sub_bytes // slices)
+                    if d == 0 and s == slices - 1:
+                        # the block also held the sub-block that stays
+                        _capi.check(self._lib.qj_copy_async(h, ctypes.c_void_p(out + mine * sub_bytes),
+                                                            ctypes.c_void_p(ptr + mine * sub_bytes), sub_bytes))
+                on_side(step)
+        on_side(lambda: self._peer_handshake(comm, [rank_of(a) for a in everyone]))   # every pull out of this shard is done
         fin = torch.cuda.Event()
         fin.record(side)
-        if defer:
-            self._pending_exchange = {"k": k, "mine": mine, "order": order, "arrived": arrived, "fin": fin, "ptr": out}
-        else:
-            main.wait_event(fin)
+        main.wait_event(fin)
         return spare, moved
 
     def shard_exchange(self, shard, nlocal, lbit, peer, is_upper, comm, chunk_bytes=1 << 29):

@@ -568,12 +568,9 @@ class DistributedState:
                 lbits = nxt.local_bits if isinstance(nxt, MultiExchange) else [nxt.local_bit]
                 rbits = nxt.rank_bits if isinstance(nxt, MultiExchange) else [nxt.rank_bit]
                 before = self.shard
-                after = steps_list[pos + 2] if pos + 2 < len(steps_list) else None
-                # (another segment follows: its first pass takes the sub-blocks as they arrive)
                 self.shard, moved = b.run_segment_then_exchange(self.shard, self.nlocal, step, lbits, rbits,
                                                                 self.rank, self.comm, self.swap_chunk_bytes,
-                                                                spare=self.spare_buffer(),
-                                                                defer=isinstance(after, LocalSegment))
+                                                                spare=self.spare_buffer())
                 if self.shard is not before:      # exchanged out of place: the old shard is the next spare
                     self._spare = before
                 self.stats["local_segments"] += 1

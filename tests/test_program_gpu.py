@@ -196,3 +196,92 @@ def test_program_from_zero_ignores_the_buffer(n, dtype):
         assert out[0] == 1 and not np.any(out[1:])
     finally:
         b.set_dtype("complex128")
+
+
+@pytest.mark.parametrize("dtype", ["complex128", "complex64"])
+@pytest.mark.parametrize("pieces", [1, 2, 8])
+def test_launches_by_tile_range_and_out_of_place(dtype, pieces):
+    """`qj_program_run_tiles` over a partition of the tiles equals the whole launch, and
+    `qj_program_run_tiles_to` stores the same amplitudes into another buffer (the distributed layer
+    pipelines the last pass before an exchange this way)."""
+    import ctypes
+
+    from qibojit_b200 import _capi
+
+    b = backend()
+    n = 18
+    glist = random_circuit_gates(n, 60, 11)
+    st = R.random_state(n, dtype, 4)
+    b.set_dtype(dtype)
+    try:
+        prog = planner.Program(b, glist, n, dtype=dtype)
+        whole = b.to_numpy(prog.run(b.cast(st, dtype=dtype, copy=True)))
+        assert [s[0] for s in prog.segments] == ["program"]
+        handle, h = prog.segments[0][1], b._handle()
+        nl = ctypes.c_int64()
+        _capi.check(b._lib.qj_program_stats(handle, ctypes.byref(nl), None, None))
+        last = int(nl.value) - 1
+        geom = (ctypes.c_int64 * 12)()
+        _capi.check(b._lib.qj_program_launch_geometry(handle, last, geom))
+        ntiles = int(geom[3])
+        assert ntiles % pieces == 0
+        d = b.cast(st, dtype=dtype, copy=True)
+        other = b.cast(np.zeros_like(st), dtype=dtype, copy=True)
+        if last > 0:
+            _capi.check(b._lib.qj_program_run_ex(h, handle, d.data_ptr(), 0, last, 0))
+        step = ntiles // pieces
+        # even pieces in place, odd pieces into the other buffer
+        for i in range(pieces):
+            if i % 2 == 0:
+                _capi.check(b._lib.qj_program_run_tiles(h, handle, d.data_ptr(), last, i * step, step))
+            else:
+                _capi.check(b._lib.qj_program_run_tiles_to(h, handle, d.data_ptr(), ctypes.c_void_p(other.data_ptr()),
+                                                           last, i * step, step))
+        got_d, got_o = b.to_numpy(d), b.to_numpy(other)
+        # tiles are numbered by the index bits outside the tile, least significant first: piece i
+        # holds the amplitudes whose outside bits spell a tile number in its range
+        T_r, hib = int(geom[1]), [int(v) for v in geom[4:12] if v >= 0]
+        outside = [q for q in range(T_r, n) if q not in hib]
+        idx = np.arange(1 << n)
+        tile = np.zeros(1 << n, dtype=np.int64)
+        for j, q in enumerate(outside):
+            tile |= ((idx >> q) & 1) << j
+        piece_of = tile // step
+        in_place = piece_of % 2 == 0
+        np.testing.assert_array_equal(got_d[in_place], whole[in_place])
+        np.testing.assert_array_equal(got_o[~in_place], whole[~in_place])
+        assert not got_o[in_place].any()
+        # out of range
+        assert b._lib.qj_program_run_tiles(h, handle, d.data_ptr(), last, ntiles, 1) != 0
+        prog.close()
+    finally:
+        b.set_dtype("complex128")
+
+
+def test_peer_handshake_and_async_copy_on_one_device():
+    """`qj_peer_handshake` against this device's own flag words (the peer is this rank: the epoch it
+    waits for is the one it publishes) and `qj_copy_async` between two buffers."""
+    import ctypes
+
+    import torch
+
+    from qibojit_b200 import _capi
+
+    b = backend()
+    h = b._handle()
+    flags = torch.zeros(64, dtype=torch.int32, device=b.torch_device)
+    for epoch in (1, 2, 7):
+        slots = (ctypes.c_void_p * 2)(flags.data_ptr() + 4 * 3, flags.data_ptr() + 4 * 5)
+        src = (ctypes.c_int32 * 2)(3, 5)
+        eps = (ctypes.c_uint32 * 2)(epoch, epoch + 100)
+        _capi.check(b._lib.qj_peer_handshake(h, ctypes.c_void_p(flags.data_ptr()), slots, src, eps, 2,
+                                             ctypes.c_double(5.0)))
+        b.synchronize()
+        got = flags.cpu().numpy()
+        assert got[3] == epoch and got[5] == epoch + 100 and got[[0, 1, 2, 4]].sum() == 0
+    assert b._lib.qj_peer_handshake(h, ctypes.c_void_p(flags.data_ptr()), slots, src, eps, 0, ctypes.c_double(1.0)) != 0
+    a = torch.arange(1 << 20, dtype=torch.float64, device=b.torch_device)
+    c = torch.zeros_like(a)
+    _capi.check(b._lib.qj_copy_async(h, ctypes.c_void_p(c.data_ptr()), ctypes.c_void_p(a.data_ptr()), a.numel() * 8))
+    b.synchronize()
+    assert torch.equal(a, c)

@@ -114,24 +114,44 @@ def main():
         b.set_dtype(dtype)
         n = 20
         tol = 1e-5 if dtype == "complex64" else 1e-12
-        for name, circuit in (("qft", circuits.qft(n)), ("supremacy", circuits.supremacy(n, depth=6)),
-                              ("variational", circuits.variational(n))):
+        from tests.circuits_random import random_circuit_gates
+
+        cases = [("qft", circuits.qft(n)), ("supremacy", circuits.supremacy(n, depth=6)),
+                 ("variational", circuits.variational(n))]
+        # the last pass before the exchange works on the qubits that leave (all of them / one of them):
+        # exchanged bits inside the pass's tile
+        g = world.bit_length() - 1
+        for part in (False, True):
+            q = [gates.H(i) for i in range(g, n)]
+            for i, t in enumerate(list(range(g, 2 * g))[: (1 if part else g)]):
+                q += [gates.fSim(t, n - 1 - i, 0.3 + i, 0.7), gates.RY(t, 0.4)]
+            q += [gates.H(i) for i in range(g)] + [gates.RY(i, 0.1 * i) for i in range(n) if not g <= i < 2 * g]
+            cc = Circuit(n)
+            cc.add(q)
+            cases.append(("leaving-" + ("one" if part else "all"), cc))
+        for seed in range(6):
+            rc = Circuit(n)
+            rc.add([gates.H(q) for q in range(n)] + random_circuit_gates(n, 150, 100 + seed))
+            cases.append((f"random-{seed}", rc))
+        for name, circuit in cases:
             outs = {}
             for mode in ("1", "0"):
                 os.environ["QJ_OVERLAP_EXCHANGE"] = mode
                 before = getattr(b, "overlapped_exchanges", 0)
-                before_arr = getattr(b, "pipelined_arrivals", 0)
+                before_in = getattr(b, "overlapped_inside_tile", 0)
                 ds = DistributedState(b, n, comm=Comm(), dtype=dtype)
                 ds.execute(circuit.queue)
                 outs[mode] = (ds.to_numpy_full(), getattr(b, "overlapped_exchanges", 0) - before,
-                              getattr(b, "pipelined_arrivals", 0) - before_arr)
+                              getattr(b, "overlapped_inside_tile", 0) - before_in, ds.stats["exchanges"])
                 b.release_peer_mappings()
             os.environ["QJ_OVERLAP_EXCHANGE"] = "1"
             same = bool(np.array_equal(outs["1"][0], outs["0"][0]))
             err = float(np.abs(outs["1"][0] - _reference_state(circuit, dtype)).max())
             # (the variational circuit's exchanges are not on the shard's top bits: it takes the plain order)
-            good = same and err < tol and outs["0"][1] == 0 and (outs["1"][1] >= 1 or name == "variational")
-            say(rank, f"pipelined exchange {dtype:10s} {name:12s}: engaged {outs['1'][1]}x (next pass fed as it arrives: {outs['1'][2]}x), identical to the plain order: {same}, "
+            good = same and err < tol and outs["0"][1] == 0 and (outs["1"][1] >= 1 or name not in ("qft", "supremacy"))
+            if name.startswith("leaving"):
+                good = good and outs["1"][2] >= 1
+            say(rank, f"pipelined exchange {dtype:10s} {name:12s}: {outs['1'][3]} exchanges, pipelined {outs['1'][1]}x ({outs['1'][2]}x with exchanged bits inside the tile), identical to the plain order: {same}, "
                       f"max|err| vs reference {err:.2e} {'ok' if good else 'FAIL'}")
             ok &= good
     b.set_dtype("complex128")

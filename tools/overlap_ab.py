@@ -33,7 +33,6 @@ def main():
             state = DistributedState(b, n, comm=Comm(), dtype=dtype)
             plan = state.plan(circuit.queue)
             before = getattr(b, "overlapped_exchanges", 0)
-            before_arr = getattr(b, "pipelined_arrivals", 0)
             for _ in range(2):
                 state.reset(); state.run(plan)
             torch.cuda.synchronize(); dist.barrier()
@@ -54,8 +53,7 @@ def main():
                 norm = f"PARITY FAILED: {exc}"
             if rank == 0:
                 print(f"{case} overlap={on} slices={slices or '-'}: {float(ms[0]):.1f} ms per circuit, "
-                      f"pipelined exchanges {getattr(b, 'overlapped_exchanges', 0) - before} "
-                      f"(arrivals fed to the next pass {getattr(b, 'pipelined_arrivals', 0) - before_arr}), {norm}", flush=True)
+                      f"pipelined exchanges {getattr(b, 'overlapped_exchanges', 0) - before}, {norm}", flush=True)
             state.shard = None
             state._spare = None
             del state
