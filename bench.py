@@ -704,6 +704,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary workloads of the default run")
+    ap.add_argument("--no-n1", action="store_true",
+                    help="--gpus N > 1: skip the single-GPU run of the same circuit on rank 0 (the N = 1 point)")
     ap.add_argument("--measure", action="store_true",
                     help="append the measurement leg (probabilities, 10^6 shots, collapse); default for --workload qv")
     args = ap.parse_args()

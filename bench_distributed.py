@@ -303,6 +303,29 @@ def run_distributed(args, backend, world, rank):
     nqubits = args.nqubits or cfg["nqubits"]
     dtype = args.dtype or cfg["dtype"]
 
+    # ---- the N = 1 point of the same circuit (strong scaling): rank 0's GPU alone, unsharded
+    # multi-gate passes, before any shard is allocated; the other ranks wait
+    n1 = None
+    amp = 16 if dtype == "complex128" else 8
+    if not getattr(args, "no_n1", False) and (amp << nqubits) <= 150e9:
+        if rank == 0:
+            try:
+                from bench import check_parity, time_program
+
+                rec, st, _ = time_program(backend, workload, nqubits, dtype, min(args.steps, 2), 1)
+                par = check_parity(backend, st, workload, nqubits, dtype)
+                del st
+                n1 = {"value": rec["value"], "unit": "gates/s", "ms_per_step": rec["ms_per_step"], "passes": rec["passes"],
+                      "parity_max_abs_err": par.get("max_abs_err"),
+                      "how": "the same circuit on rank 0's GPU alone (unsharded multi-gate passes), timed in this "
+                             "process before the sharded run; also `secondary` of the --gpus 1 line"}
+            except AssertionError:
+                raise
+            except Exception as exc:      # (e.g. the device is shared and short of memory)
+                n1 = {"error": f"{type(exc).__name__}: {exc}"}
+            torch.cuda.empty_cache()
+        dist.barrier()
+
     primary, circuit = time_sharded(backend, workload, nqubits, dtype, args.steps, args.warmup, world, rank,
                                     measure=(workload == "qv" or args.measure))
     e2e = time_sharded_e2e(backend, circuit, nqubits, dtype, min(args.steps, 2))
@@ -340,7 +363,7 @@ def run_distributed(args, backend, world, rank):
                        "parallelism": f"state sharded over {world} ranks on the top {world.bit_length() - 1} qubits; "
                                       "qubit exchanges over NVLink (pairwise half-shard swap for one qubit, "
                                       "all-to-all of (2^k-1)/2^k of a shard for k qubits)",
-                       "strong_scaling_n1": "the N = 1 point of this workload is `secondary.supremacy` of the "
+                       "strong_scaling_n1": n1 if n1 is not None else "the N = 1 point of this workload is `secondary.supremacy` of the "
                                             "`--gpus 1` line (its primary workload is QFT-33 complex128)",
                        "l2_policy": "shards are far larger than the 126 MB L2; no flush needed",
                        "timing": "CUDA events on the launch stream, max over ranks"},

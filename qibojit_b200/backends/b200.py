@@ -914,11 +914,17 @@ class B200Backend(_QiboBackend):
             _capi.check(self._lib.qj_copy_async(h, ctypes.c_void_p(out + a * sub_bytes + off),
                                                 ctypes.c_void_p(src_ptrs[rank_of(a)] + mine * sub_bytes + off), nbytes))
 
+        trace = os.environ.get("QJ_OVERLAP_TRACE") == "1"
+        if trace:
+            t_begin, t_passes, t_end = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            t_begin.record(main)
         my_block = block_of(mine)
         everyone = []
         for d in list(range(1, 1 << nfree)) + [0]:
             block = my_block ^ d
-            partners = [a for a in range(1 << k) if block_of(a) == block and a != mine]
+            # (same XOR offsets on every rank, in the same order: each pull of a step is a perfect
+            # matching over the ranks -- nobody's links serve two readers while a sibling's idle)
+            partners = [mine ^ x for x in range(1, 1 << k) if block_of(x) == d]
             everyone += partners
             if not partners:
                 # the block is this rank's own sub-block: from the shard straight into the new buffer
@@ -940,10 +946,17 @@ class B200Backend(_QiboBackend):
                         _capi.check(self._lib.qj_copy_async(h, ctypes.c_void_p(out + mine * sub_bytes),
                                                             ctypes.c_void_p(ptr + mine * sub_bytes), sub_bytes))
                 on_side(step)
+        if trace:
+            t_passes.record(main)
         on_side(lambda: self._peer_handshake(comm, [rank_of(a) for a in everyone]))   # every pull out of this shard is done
         fin = torch.cuda.Event()
         fin.record(side)
         main.wait_event(fin)
+        if trace:
+            t_end.record(main)
+            t_end.synchronize()
+            self.overlap_trace = {"last_pass_ms": t_begin.elapsed_time(t_passes), "total_ms": t_begin.elapsed_time(t_end),
+                                  "blocks": 1 << nfree, "slices": slices, "inside_bits": len(inside)}
         return spare, moved
 
     def shard_exchange(self, shard, nlocal, lbit, peer, is_upper, comm, chunk_bytes=1 << 29):

@@ -210,7 +210,7 @@ def test_launches_by_tile_range_and_out_of_place(dtype, pieces):
 
     b = backend()
     n = 18
-    glist = random_circuit_gates(n, 60, 11)
+    glist = random_circuit_gates(n, 60, 11, with_raw=False)
     st = R.random_state(n, dtype, 4)
     b.set_dtype(dtype)
     try:

@@ -51,6 +51,9 @@ def main():
                 norm = f"parity {par.get('max_abs_err')} ({'pinned' if par.get('pinned', True) else 'sum only'})"
             except AssertionError as exc:
                 norm = f"PARITY FAILED: {exc}"
+            if on == "1" and os.environ.get("QJ_OVERLAP_TRACE") == "1":
+                state.reset(); state.run(plan)
+                print(f"   rank {rank} trace {getattr(b, 'overlap_trace', None)}", flush=True)
             if rank == 0:
                 print(f"{case} overlap={on} slices={slices or '-'}: {float(ms[0]):.1f} ms per circuit, "
                       f"pipelined exchanges {getattr(b, 'overlapped_exchanges', 0) - before}, {norm}", flush=True)
