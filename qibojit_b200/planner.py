@@ -216,23 +216,29 @@ class _DiagAcc:
         self.table = np.ones(1, dtype=np.complex128)
 
     def absorb(self, op):
-        # controls of a diagonal op are table bits whose 0-branch is the identity
+        # controls of a diagonal op are table bits whose 0-branch is the identity: with the targets on
+        # the low table bits the controlled entries are the top block
         obits = list(op.targets) + list(op.controls)
-        otab = np.ones(1 << len(obits), dtype=np.complex128)
-        nt = len(op.targets)
-        cmask = ((1 << len(op.controls)) - 1) << nt
-        idx = np.arange(1 << len(obits))
-        sel = (idx & cmask) == cmask
-        otab[sel] = np.asarray(op.data, dtype=np.complex128)[idx[sel] & ((1 << nt) - 1)]
+        nt, nc = len(op.targets), len(op.controls)
+        data = np.asarray(op.data, dtype=np.complex128)
+        if nc:
+            otab = np.ones(1 << (nt + nc), dtype=np.complex128)
+            otab[((1 << nc) - 1) << nt:] = data[:1 << nt]
+        else:
+            otab = data[:1 << nt]
         for b in obits:
             if b not in self.bits:
                 self.bits.append(b)
-                self.table = np.tile(self.table, 2)
-        i = np.arange(self.table.size)
-        gi = np.zeros_like(i)
-        for k, b in enumerate(obits):
-            gi |= ((i >> self.bits.index(b)) & 1) << k
-        self.table = self.table * otab[gi]
+                self.table = np.concatenate((self.table, self.table))
+        # table[i] *= otab[the bits of i at the op's positions]: a broadcast product over the table
+        # seen as a 2 x ... x 2 array (axis a <-> table bit n - 1 - a)
+        n, m = len(self.bits), len(obits)
+        axis_of = [n - 1 - self.bits.index(b) for b in obits]       # table axis of op bit k
+        order = sorted(range(m), key=lambda k: axis_of[k])
+        factor = otab.reshape((2,) * m).transpose([m - 1 - k for k in order])
+        used = set(axis_of)
+        factor = factor.reshape([2 if a in used else 1 for a in range(n)])
+        self.table = (self.table.reshape((2,) * n) * factor).reshape(-1)
 
     def finish(self):
         """-> PlanOp with control-like bits split off (None when the product is the identity)."""
@@ -240,11 +246,10 @@ class _DiagAcc:
         controls = []
         j = 0
         while j < len(bits):
-            i = np.arange(table.size)
-            zero = table[((i >> j) & 1) == 0]
-            if np.all(zero == 1.0):
+            nd = table.reshape(1 << (len(bits) - 1 - j), 2, 1 << j)      # middle axis = table bit j
+            if np.all(nd[:, 0, :] == 1.0):
                 controls.append(bits.pop(j))
-                table = table[((i >> j) & 1) == 1]
+                table = np.ascontiguousarray(nd[:, 1, :]).reshape(-1)
             else:
                 j += 1
         if np.all(table == 1.0):

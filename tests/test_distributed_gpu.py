@@ -118,3 +118,32 @@ def test_single_rank_layout_and_measurement(dtype):
             execute_distributed_circuit(b, c, initial_state="zeros", comm=_OneRank())
     finally:
         b.set_dtype("complex128")
+
+
+def test_multi_rank_parity_under_torchrun():
+    """The whole of tools/dist_check.py on two ranks of this box (one process per GPU, NCCL + CUDA
+    IPC): distributed parity on both exchange transports, layout / collapse / sampling on the sharded
+    state, the pipelined out-of-place exchange bit for bit against the plain order, two devices
+    driven from one process.  Needs two GPUs; a single-GPU box skips it."""
+    import os
+    import socket
+    import subprocess
+    import sys
+
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs on one box")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    env = dict(os.environ, QJ_NLOCAL="24")          # (small shards for the bandwidth section)
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", str(port),
+                          os.path.join(root, "tools", "dist_check.py")],
+                         capture_output=True, text=True, timeout=900, cwd=root, env=env)
+    tail = "\n".join((out.stdout + out.stderr).splitlines()[-40:])
+    assert out.returncode == 0, tail
+    assert "rank 0: ALL OK" in out.stdout and "rank 1: ALL OK" in out.stdout, tail
+    assert "FAIL" not in out.stdout, tail
