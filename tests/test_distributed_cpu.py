@@ -206,3 +206,40 @@ def test_distributed_plans_fuzz_in_one_process(world):
             got, _ = run_virtual(glist, n, world, dtype, **kw)
             np.testing.assert_allclose(got, ref, rtol=0, atol=1e-12 if dtype == "complex128" else 2e-5,
                                        err_msg=f"case {case} n={n} {dtype} {kw}")
+
+
+def test_tile_split_over_exchanged_bits():
+    """`B200Backend._tile_split` (host logic of the pipelined exchange): the exchanged top bits that
+    lie outside a launch's tile enumerate contiguous tile ranges; checked against the kernel's tile
+    numbering (index bits outside the tile, least significant first) by brute force."""
+    import numpy as np
+
+    from qibojit_b200.backends.b200 import B200Backend
+
+    split = B200Backend._tile_split
+    nlocal = 14
+    rng = np.random.default_rng(3)
+    idx = np.arange(1 << nlocal)
+    for trial in range(60):
+        r = int(rng.integers(2, 6))
+        nh = int(rng.integers(0, 4))
+        hibits = sorted(int(b) for b in rng.choice(np.arange(r, nlocal), size=nh, replace=False))
+        T = r + nh
+        geom = {"T": T, "r": r, "ntiles": 1 << (nlocal - T), "hibits": hibits}
+        outside = [b for b in range(r, nlocal) if b not in hibits]
+        tile = np.zeros_like(idx)
+        for j, b in enumerate(outside):
+            tile |= ((idx >> b) & 1) << j
+        for ntop in (1, 2, 3):
+            got = split(geom, nlocal, ntop)
+            assert got is not None
+            free, per = got
+            assert free == [i for i in range(ntop) if (nlocal - ntop + i) not in hibits]
+            assert per << len(free) == geom["ntiles"]
+            value = np.zeros_like(idx)
+            for j, i in enumerate(free):
+                value |= ((idx >> (nlocal - ntop + i)) & 1) << j
+            assert np.array_equal(tile // per, value)      # tile range v <-> free bits spell v
+    # the contiguous part of the tile reaches into the exchanged bits: no split
+    assert split({"T": 12, "r": 12, "ntiles": 4, "hibits": []}, 14, 3) is None
+    assert split({"T": 12, "r": 11, "ntiles": 4, "hibits": [12]}, 14, 3) == ([0, 2], 1)
