@@ -8,11 +8,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libqibojit_b200.so")
-SOURCES = ["capi.cu", "gate_kernels.cu", "tile_kernels.cu", "ops_kernels.cu", "pass_kernels.cu"]
-HEADERS = ["common.cuh", os.path.join("..", "..", "include", "qibojit_b200.h")]
+SOURCES = ["pass_kernels.cu", "pass_kernels_f32.cu", "capi.cu", "gate_kernels.cu", "tile_kernels.cu", "ops_kernels.cu"]
+HEADERS = ["common.cuh", "pass_device.cuh", os.path.join("..", "..", "include", "qibojit_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "128",
+    "-Xcompiler", "-fPIC", "-diag-suppress", "128",
 ]
 
 
@@ -36,13 +36,32 @@ def build(force=False, verbose=False):
     if not force and not is_stale():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH]
-    cmd += [os.path.join(CSRC, s) for s in SOURCES]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    if verbose:
-        print(res.stderr)
+    import tempfile
+
+    # one nvcc per translation unit, all at once (the two instantiations of the pass kernel take
+    # minutes of ptxas each), then one link
+    with tempfile.TemporaryDirectory(prefix="qj_build_") as tmp:
+        extra = ["-Xptxas", "-v"] if verbose else []
+        procs = []
+        for src in SOURCES:
+            obj = os.path.join(tmp, src.replace(".cu", ".o"))
+            cmd = [_nvcc()] + NVCC_FLAGS + extra + ["-c", os.path.join(CSRC, src), "-o", obj]
+            procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        logs, failed = [], []
+        for src, obj, proc in procs:
+            out = proc.communicate()[0]
+            logs.append(out)
+            if proc.returncode != 0:
+                failed.append(f"{src}:\n{out}")
+        if failed:
+            raise RuntimeError("nvcc failed:\n" + "\n".join(failed))
+        link = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH]
+        link += [obj for _, obj, _ in procs]
+        res = subprocess.run(link, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("link failed:\n" + res.stdout + res.stderr)
+        if verbose:
+            print("\n".join(logs))
     return LIB_PATH
 
 
